@@ -1,0 +1,344 @@
+// isx_math.cuh — float math with the SAME BITS as the libm the reference binds.
+//
+// The reference sim core imports exactly sincosf, tanf, atan2f, hypotf, fmodf (+ expf, host only)
+// from glibc (SURVEY.md §7 hard part 1).  Collision flags and lidar hit indices are knife-edge
+// functions of poses, so "within 1 ulp" device intrinsics are not good enough for bit-exact parity.
+// These are restatements of the PUBLISHED algorithms glibc 2.39 ships for those entry points:
+//
+//   sincosf : ARM Optimized Routines sincosf (Szabolcs Nagy, 2018; glibc sysdeps/ieee754/flt-32/
+//             s_sincosf.{c,h}, s_sincosf_data.c): double-precision range reduction by pi/2 and two
+//             degree-(7,8) polynomials on [-pi/4, pi/4].  glibc dispatches to an FMA build on every
+//             FMA-capable x86-64 CPU; the operation pairing below (which products are fused) is that
+//             build's, so results agree bit-for-bit with it.
+//   tanf    : fdlibm k_tanf.c (Sun, 1993; float port by Ian Taylor) + the sincosf reduction.
+//   atan2f  : fdlibm e_atan2f.c / s_atanf.c.
+//   hypotf  : glibc >= 2.35 e_hypotf.c: sqrt in double of the exact squares.
+//   fmodf   : exact by definition (CUDA fmodf has 0 ulp error); used as is.
+//
+// Every function is __host__ __device__: the host build is swept against this machine's libm in
+// tests/test_math_host.py (exhaustively for the 1-argument functions), the device build is compared
+// with the host build in tests/test_gpu_math.py.  REQUIRES float/double contraction OFF
+// (nvcc -fmad=false, g++ -ffp-contract=off): fused operations are written explicitly with fma().
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define ISX_HD __host__ __device__ __forceinline__
+#else
+#define ISX_HD static inline
+#endif
+
+namespace isx {
+
+constexpr float PI_F = 3.14159265358979323846f;       // 0x40490fdb, as Car.cpp:7
+constexpr float TWO_PI_F = 2.0f * PI_F;
+
+ISX_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+ISX_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+ISX_HD int f2i_rz(float f) {      // C's (int)f for in-range values
+#if defined(__CUDA_ARCH__)
+    return __float2int_rz(f);
+#else
+    return (int)f;
+#endif
+}
+ISX_HD int d2i_rz(double d) {
+#if defined(__CUDA_ARCH__)
+    return __double2int_rz(d);
+#else
+    return (int)d;
+#endif
+}
+ISX_HD float fsqrt_rn(float x) {
+#if defined(__CUDA_ARCH__)
+    return __fsqrt_rn(x);
+#else
+    return sqrtf(x);
+#endif
+}
+ISX_HD float fdiv_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+ISX_HD double dsqrt_rn(double x) {
+#if defined(__CUDA_ARCH__)
+    return __dsqrt_rn(x);
+#else
+    return sqrt(x);
+#endif
+}
+
+// ---------------------------------------------------------------- sincosf
+// 4/pi as 24 overlapping 32-bit words (192 bits), for |x| >= 120.
+ISX_HD uint32_t inv_pio4_word(int i) {
+    const uint32_t t[24] = {
+        0xa2u, 0xa2f9u, 0xa2f983u, 0xa2f9836eu, 0xf9836e4eu, 0x836e4e44u, 0x6e4e4415u, 0x4e441529u,
+        0x441529fcu, 0x1529fc27u, 0x29fc2757u, 0xfc2757d1u, 0x2757d1f5u, 0x57d1f534u, 0xd1f534ddu, 0xf534ddc0u,
+        0x34ddc0dbu, 0xddc0db62u, 0xc0db6295u, 0xdb629599u, 0x6295993cu, 0x95993c43u, 0x993c4390u, 0x3c439041u};
+    return t[i];
+}
+
+// Reduce y to xr in [-pi/4, pi/4] and quadrant n; returns false for inf/nan.  `sgn_extra` is the
+// sign bit that the large-argument path folds into the quadrant (0 elsewhere).
+ISX_HD bool sincos_reduce(float y, double* xr, int* n, int* sgn_extra) {
+    const double HPI_INV = 0x1.45F306DC9C883p+23;   // 2/pi * 2^24
+    const double HPI = 0x1.921FB54442D18p0;
+    const uint32_t iy = f2u(y);
+    const uint32_t top = (iy >> 20) & 0x7ffu;
+    const double x = (double)y;
+    *sgn_extra = 0;
+    if (top < 0x3f4u) {                 // |y| < 0.75 (top-12-bit compare with pi/4)
+        *xr = x; *n = 0;
+        return true;
+    }
+    if (top < 0x42fu) {                 // |y| < 120
+        const double r = x * HPI_INV;
+        const int q = (d2i_rz(r) + 0x800000) >> 24;
+        *xr = fma(-(double)q, HPI, x);
+        *n = q;
+        return true;
+    }
+    if (top < 0x7f8u) {                 // finite: 192-bit 4/pi table
+        const int idx = (int)((iy >> 26) & 15u);
+        const int shift = (int)((iy >> 23) & 7u);
+        uint32_t xi = (iy & 0xffffffu) | 0x800000u;
+        xi <<= shift;
+        uint64_t res0 = (uint64_t)(uint32_t)(xi * inv_pio4_word(idx));
+        const uint64_t res1 = (uint64_t)xi * inv_pio4_word(idx + 4);
+        const uint64_t res2 = (uint64_t)xi * inv_pio4_word(idx + 8);
+        res0 = (res2 >> 32) | (res0 << 32);
+        res0 += res1;
+        const uint64_t q = (res0 + (1ULL << 61)) >> 62;
+        res0 -= q << 62;
+        *xr = (double)(int64_t)res0 * 0x1.921FB54442D18p-62;
+        *n = (int)q;
+        *sgn_extra = (int)(iy >> 31);
+        return true;
+    }
+    return false;
+}
+
+ISX_HD void sincosf_(float y, float* sinp, float* cosp) {
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5,
+                 C3 = -0x1.6c087e89a359dp-10, C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    if (((f2u(y) >> 20) & 0x7ffu) < 0x398u) {   // |y| < 2^-12
+        *sinp = y; *cosp = 1.0f;
+        return;
+    }
+    double xr; int n, se;
+    if (!sincos_reduce(y, &xr, &n, &se)) {
+        const float nan = y - y;
+        *sinp = nan; *cosp = nan;
+        return;
+    }
+    const int q = n + se;
+    // sign table {1,-1,-1,1}[q&3]; the second coefficient set (q&2) is the first with c0..c4 negated
+    const double sg = (((q & 3) == 1) || ((q & 3) == 2)) ? -1.0 : 1.0;
+    const double xs = xr * sg;
+    const double x2 = xr * xr;
+    const double x3 = x2 * xs;
+    const double x4 = x2 * x2;
+    const double s1v = fma(x2, S3, S2);
+    const double c2v = fma(x2, C4, C3);
+    const double x5 = x2 * x3;
+    const double x6 = x2 * x4;
+    const double c1v = fma(x2, C1, C0);
+    const double sv = fma(x3, S1, xs);
+    const double cv = fma(x4, C2, c1v);
+    const float fs = (float)fma(s1v, x5, sv);
+    float fc = (float)fma(c2v, x6, cv);
+    if (q & 2) fc = -fc;
+    if (n & 1) { *sinp = fc; *cosp = fs; }
+    else       { *sinp = fs; *cosp = fc; }
+}
+
+// ---------------------------------------------------------------- tanf
+ISX_HD float kernel_tanf(float x, float y, int iy) {
+    const float T0 = u2f(0x3eaaaaabu), T1 = u2f(0x3e088889u), T2 = u2f(0x3d5d0dd1u), T3 = u2f(0x3cb327a4u),
+                T4 = u2f(0x3c11371fu), T5 = u2f(0x3b6b6916u), T6 = u2f(0x3abede48u), T7 = u2f(0x3a1a26c8u),
+                T8 = u2f(0x398137b9u), T9 = u2f(0x38a3f445u), T10 = u2f(0x3895c07au), T11 = u2f(0xb79bae5fu),
+                T12 = u2f(0x37d95384u);
+    const float pio4 = u2f(0x3f490fdau), pio4lo = u2f(0x33222168u);
+    const uint32_t hx = f2u(x);
+    const uint32_t ix = hx & 0x7fffffffu;
+    if (ix < 0x39000000u) {                 // |x| < 2^-13
+        if (f2i_rz(x) == 0) {
+            if ((ix | (uint32_t)(iy + 1)) == 0u) return fdiv_rn(1.0f, fabsf(x));
+            else if (iy == 1) return x;
+            else return fdiv_rn(-1.0f, x);
+        }
+    }
+    const bool big = ix >= 0x3f2ca140u;     // |x| >= 0.6744
+    if (big) {
+        if ((int32_t)hx < 0) { x = -x; y = -y; }
+        const float z0 = pio4 - x;
+        const float w0 = pio4lo - y;
+        x = z0 + w0; y = 0.0f;
+        if (fabsf(x) < 0x1p-13f) {
+            const int sgn = 1 - (int)((hx >> 30) & 2u);
+            return (float)(sgn * iy) * (1.0f - (float)(2 * iy) * x);
+        }
+    }
+    const float z = x * x;
+    const float w = z * z;
+    const float r0 = T1 + w * (T3 + w * (T5 + w * (T7 + w * (T9 + w * T11))));
+    const float v0 = z * (T2 + w * (T4 + w * (T6 + w * (T8 + w * (T10 + w * T12)))));
+    const float s = z * x;
+    float r = y + z * (s * (r0 + v0) + y);
+    r += T0 * s;
+    const float ww = x + r;
+    if (big) {
+        const float v = (float)iy;
+        const int sgn = 1 - (int)((hx >> 30) & 2u);
+        return (float)sgn * (v - 2.0f * (x - (fdiv_rn(ww * ww, ww + v) - r)));
+    }
+    if (iy == 1) return ww;
+    // -1/(x+r) with extra care
+    const float zz = u2f(f2u(ww) & 0xfffff000u);
+    const float vv = r - (zz - x);
+    const float a = fdiv_rn(-1.0f, ww);
+    const float t = u2f(f2u(a) & 0xfffff000u);
+    const float ss = 1.0f + t * zz;
+    return t + a * (ss + t * vv);
+}
+
+ISX_HD float tanf_(float x) {
+    const uint32_t ix = f2u(x) & 0x7fffffffu;
+    if (ix <= 0x3f490fdau) return kernel_tanf(x, 0.0f, 1);    // |x| <= pi/4
+    if (ix >= 0x7f800000u) return x - x;                       // inf/nan
+    double xr; int n, se;
+    sincos_reduce(x, &xr, &n, &se);       // top>=0x3f4 here, so always the reducing branches
+    if (se) xr = -xr;                     // large path reduces |x|
+    // the medium branch of glibc's tanf does NOT fuse x - n*hpi (baseline build): redo it unfused
+    if (((f2u(x) >> 20) & 0x7ffu) < 0x42fu) {
+        const double HPI = 0x1.921FB54442D18p0;
+        xr = (double)x - (double)n * HPI;
+    }
+    const float y0 = (float)xr;
+    const float y1 = (float)(xr - (double)y0);
+    return kernel_tanf(y0, y1, 1 - ((n & 1) << 1));
+}
+
+// ---------------------------------------------------------------- atanf / atan2f
+ISX_HD float atanf_(float x) {
+    const float aT0 = u2f(0x3eaaaaabu), aT1 = u2f(0xbe4ccccdu), aT2 = u2f(0x3e124925u), aT3 = u2f(0xbde38e38u),
+                aT4 = u2f(0x3dba2e6eu), aT5 = u2f(0xbd9d8795u), aT6 = u2f(0x3d886b35u), aT7 = u2f(0xbd6ef16bu),
+                aT8 = u2f(0x3d4bda59u), aT9 = u2f(0xbd15a221u), aT10 = u2f(0x3c8569d7u);
+    const uint32_t hx = f2u(x);
+    const uint32_t ix = hx & 0x7fffffffu;
+    float hi = 0.0f, lo = 0.0f;
+    int id;
+    if (ix >= 0x4c000000u) {               // |x| >= 2^25
+        if (ix > 0x7f800000u) return x + x;
+        const float r = u2f(0x3fc90fdau) + u2f(0x33a22168u);
+        return ((int32_t)hx > 0) ? r : -r;
+    }
+    if (ix < 0x3ee00000u) {                // |x| < 0.4375
+        if (ix < 0x31000000u) return x;    // |x| < 2^-29
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000u) {            // |x| < 1.1875
+            if (ix < 0x3f300000u) { id = 0; x = fdiv_rn(2.0f * x - 1.0f, 2.0f + x); hi = u2f(0x3eed6338u); lo = u2f(0x31ac3769u); }
+            else                  { id = 1; x = fdiv_rn(x - 1.0f, x + 1.0f);        hi = u2f(0x3f490fdau); lo = u2f(0x33222168u); }
+        } else {
+            if (ix < 0x401c0000u) { id = 2; x = fdiv_rn(x - 1.5f, 1.0f + 1.5f * x); hi = u2f(0x3f7b985eu); lo = u2f(0x33140fb4u); }
+            else                  { id = 3; x = fdiv_rn(-1.0f, x);                  hi = u2f(0x3fc90fdau); lo = u2f(0x33a22168u); }
+        }
+    }
+    const float z = x * x;
+    const float w = z * z;
+    const float s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    const float s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    if (id < 0) return x - x * (s1 + s2);
+    const float zz = hi - ((x * (s1 + s2) - lo) - x);
+    return ((int32_t)hx < 0) ? -zz : zz;
+}
+
+ISX_HD float atan2f_(float y, float x) {
+    const float tiny = u2f(0x0da24260u);   // 1.0e-30
+    const float pi_o_4 = u2f(0x3f490fdbu), pi_o_2 = u2f(0x3fc90fdbu), pi = u2f(0x40490fdbu), pi_lo = u2f(0xb3bbbd2eu);
+    const uint32_t hx = f2u(x), hy = f2u(y);
+    const uint32_t ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+    if (ix > 0x7f800000u || iy > 0x7f800000u) return x + y;
+    if (hx == 0x3f800000u) return atanf_(y);
+    const int m = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);
+    if (iy == 0u) {
+        switch (m) {
+            case 0: case 1: return y;
+            case 2: return pi + tiny;
+            default: return -pi - tiny;
+        }
+    }
+    if (ix == 0u) return ((int32_t)hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    if (ix == 0x7f800000u) {
+        if (iy == 0x7f800000u) {
+            switch (m) {
+                case 0: return pi_o_4 + tiny;
+                case 1: return -pi_o_4 - tiny;
+                case 2: return 3.0f * pi_o_4 + tiny;
+                default: return -3.0f * pi_o_4 - tiny;
+            }
+        } else {
+            switch (m) {
+                case 0: return 0.0f;
+                case 1: return -0.0f;
+                case 2: return pi + tiny;
+                default: return -pi - tiny;
+            }
+        }
+    }
+    if (iy == 0x7f800000u) return ((int32_t)hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int k = ((int)iy - (int)ix) >> 23;
+    float z;
+    if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+    else if ((int32_t)hx < 0 && k < -60) z = 0.0f;
+    else z = atanf_(fabsf(fdiv_rn(y, x)));
+    switch (m) {
+        case 0: return z;
+        case 1: return u2f(f2u(z) ^ 0x80000000u);
+        case 2: return pi - (z - pi_lo);
+        default: return (z - pi_lo) - pi;
+    }
+}
+
+// ---------------------------------------------------------------- hypotf
+ISX_HD float hypotf_(float x, float y) {
+    const uint32_t ax = f2u(x) & 0x7fffffffu, ay = f2u(y) & 0x7fffffffu;
+    if (ax >= 0x7f800000u || ay >= 0x7f800000u) {
+        if (ax == 0x7f800000u || ay == 0x7f800000u) return u2f(0x7f800000u);
+        return x + y;
+    }
+    const double dx = (double)x, dy = (double)y;
+    return (float)dsqrt_rn(dx * dx + dy * dy);
+}
+
+// ---------------------------------------------------------------- helpers used all over the sim
+ISX_HD float fmodf_(float a, float b) { return fmodf(a, b); }
+
+// wrap to [-pi, pi): IntersectionEnv.cpp:9-13, TrafficFlow.cpp:8-12, Car.cpp:33-36
+ISX_HD float wrap_angle(float a) {
+    a = fmodf_(a + PI_F, TWO_PI_F);
+    if (a < 0.0f) a += TWO_PI_F;
+    return a - PI_F;
+}
+
+}  // namespace isx
