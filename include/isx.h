@@ -1,0 +1,185 @@
+/* include/isx.h — C ABI of libisx_b200.so, the B200-native batched stepper for the intersection env.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI: its boundary is the pybind11 module
+ * `MARLEnv` (/root/reference/cpp/bindings.cpp:11-95) that /root/reference/env.py drives.  Each entry
+ * point below names the reference interface it replaces.  Signatures are plain C (pointers, sizes,
+ * no torch / STL types); all *_dev pointers are CUDA device pointers on the handle's device; every
+ * call that takes a `stream` is asynchronous and stream-ordered (`stream` is a cudaStream_t, 0 = the
+ * legacy default stream).  Every function returns 0 on success or a negative ISX_E_* code; the text of
+ * the last error on the calling thread is isx_last_error().  There is NO CPU fallback: isx_create
+ * fails (ISX_E_CUDA) when no CUDA device is usable.
+ *
+ * One handle = E env instances stepping in lockstep on one GPU (struct-of-arrays device buffers).
+ * Multi-GPU = one process and one handle per GPU with env_id_base = the shard's first global env id;
+ * results are independent of the sharding because all randomness is keyed by the GLOBAL env id.
+ */
+#ifndef ISX_H
+#define ISX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISX_ABI_VERSION 1
+#define ISX_OBS_DIM 127          /* IntersectionEnv.cpp:424 : 6 ego + 5x5 neighbours + 96 lidar */
+#define ISX_PATH_LEN 160         /* RouteGen.cpp:111-205: 50 + 60 + 50 way-points */
+#define ISX_MAX_AGENTS 32        /* egos per env */
+#define ISX_MAX_NPC 32           /* NPC slots per env (reference is unbounded; observed max 13) */
+#define ISX_MAX_RAYS 96
+#define ISX_MAX_ROUTES 64        /* traffic routes */
+
+enum { ISX_OK = 0, ISX_E_ARG = -1, ISX_E_CUDA = -2, ISX_E_ROUTE_START = -3, ISX_E_ROUTE_END = -4, ISX_E_STATE = -5 };
+
+/* status codes = the strings of IntersectionEnv.cpp:147,169,205,227,240,282,302 */
+enum { ISX_ALIVE = 0, ISX_DEAD = 1, ISX_SUCCESS = 2, ISX_CRASH_WALL = 3, ISX_CRASH_LINE = 4, ISX_CRASH_CAR = 5 };
+
+typedef struct isx_handle isx_handle;
+
+/* Everything env.py passes through IntersectionEnv(num_lanes) / configure / configure_traffic /
+ * configure_routes / reward_config.* / add_car_with_route (env.py:111-131,147-152). */
+typedef struct isx_config {
+    int32_t abi_version;         /* = ISX_ABI_VERSION */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t num_envs;            /* E on this device */
+    int32_t num_agents;          /* N egos per env (= number of ego routes) */
+    int32_t num_lanes;           /* IntersectionEnv(num_lanes), bindings.cpp:59 */
+    int32_t lidar_rays;          /* 96 = add_car_with_route (IntersectionEnv.cpp:113); 72 = default Lidar (Lidar.h:11) */
+    int32_t npc_capacity;        /* <= ISX_MAX_NPC; a spawn into a full env is dropped and counted */
+    int32_t use_team_reward;     /* configure(use_team, respawn, max_steps), IntersectionEnv.cpp:50-54 */
+    int32_t respawn_enabled;
+    int32_t max_steps;
+    int32_t traffic_flow;        /* configure_traffic(enabled, density), :56-60 */
+    float traffic_density;
+    float reward[8];             /* k_prog, v_min_ms, k_stuck, k_cv, k_co, k_succ, k_sm, alpha (Reward.h:5-14) */
+    const char *const *ego_start;     /* N lane ids, add_car_with_route(start,end) :78 */
+    const char *const *ego_end;
+    int32_t num_traffic_routes;       /* configure_routes(routes) :62-64 */
+    const char *const *traffic_start;
+    const char *const *traffic_end;
+    uint64_t seed;               /* Philox key (the reference is unseedable, TrafficFlow.cpp:278,324) */
+    int64_t env_id_base;         /* global id of local env 0 */
+    int32_t auto_reset;          /* isx_rollout / isx_step: reset an env at the start of the step after terminated|truncated */
+    int32_t reserved;
+} isx_config;
+
+/* Same fields, same meaning, same layout as oracle/isx_state.h (the checkers use this record too). */
+typedef struct isx_car_state {
+    float x, y, v, heading;      /* Car.h:9-14 */
+    float acc, steer;            /* Car.h:23-24 */
+    float prev_dist, prev_a0, prev_a1; /* Car.h:36-37 */
+    int32_t path_index;          /* Car.h:34 */
+    int32_t route;               /* ego: slot index; NPC: traffic-route index */
+    int32_t alive;               /* Car.h:27 */
+    uint32_t uid;                /* NPC spawn serial within its env */
+    int32_t intention;           /* Car.h:32 */
+} isx_car_state;
+
+typedef struct isx_traffic_events {
+    int32_t rng_draws;           /* 32-bit words consumed from the env's traffic stream this step */
+    int32_t spawn_route;         /* traffic-route index drawn, -1 if no attempt */
+    int32_t spawned;             /* 1 if an NPC was appended */
+    uint32_t removed_mask;       /* bit i: NPC at list position i (after append, before erase) was erased */
+    uint32_t collided_mask;      /* subset erased because of an NPC-NPC collision */
+    int32_t npc_count;           /* NPCs after the step */
+} isx_traffic_events;
+
+/* Non-owning device views, valid until isx_destroy.  Replaces StepResult (Reward.h:16-29) and the
+ * by-value `cars` / `traffic_cars` / `lidars` snapshots of bindings.cpp:60-62. */
+typedef struct isx_buffers {
+    float *obs;                  /* [E][N][127] f32 */
+    float *reward;               /* [E][N] */
+    uint8_t *done;               /* [E][N] */
+    uint8_t *status;             /* [E][N] ISX_* status code */
+    uint8_t *terminated;         /* [E] */
+    uint8_t *truncated;          /* [E] */
+    int32_t *agents_alive;       /* [E] */
+    int32_t *step;               /* [E] step_count */
+    uint8_t *lidar_hit;          /* [E][N][96] first-hit sample index k (distance = 4k px), 0 = no hit (250 px) */
+    /* ego state, SoA [E][N] */
+    float *ego_x, *ego_y, *ego_v, *ego_heading, *ego_steer, *ego_acc, *ego_prev_dist, *ego_prev_a0, *ego_prev_a1;
+    int32_t *ego_path_index;
+    uint8_t *ego_alive;
+    /* NPC state, SoA [E][npc_capacity]; first npc_count[e] slots are live, in list order */
+    float *npc_x, *npc_y, *npc_v, *npc_heading, *npc_steer;
+    int32_t *npc_path_index;
+    int32_t *npc_route;
+    uint32_t *npc_uid;
+    int32_t *npc_count;          /* [E] */
+    isx_traffic_events *events;  /* [E] */
+    uint32_t *tick;              /* [E] RNG tick (never reset) */
+} isx_buffers;
+
+/* Counters accumulated on the device since create / isx_stats_reset; one all-reduce(sum) over ranks
+ * gives job totals (that is the only collective this path needs). */
+typedef struct isx_stats {
+    int64_t agent_steps;
+    int64_t status_hist[6];      /* per agent-step, index = ISX_* status */
+    int64_t npc_spawned;
+    int64_t npc_removed;
+    int64_t npc_collided;
+    int64_t npc_overflow;        /* spawns dropped because the env's NPC slots were full */
+    int64_t env_resets;          /* auto-resets performed */
+    double reward_sum;
+} isx_stats;
+
+const char *isx_last_error(void);
+int isx_abi_version(void);
+
+/* IntersectionEnv(num_lanes) + configure* + reset() + add_car_with_route x N  (env.py:111-136).
+ * Unknown ego start id: the reference silently adds no car (IntersectionEnv.cpp:79-82) — a batched SoA
+ * cannot have ragged N, so here that is ISX_E_ROUTE_START.  Unknown end id: std::out_of_range ->
+ * IndexError in the reference (RouteGen.cpp:120) -> ISX_E_ROUTE_END here. */
+int isx_create(const isx_config *cfg, isx_handle **out);
+int isx_destroy(isx_handle *h);
+
+/* reset() + add_car_with_route (IntersectionEnv.cpp:66-131) for the envs whose mask byte is non-zero
+ * (all envs if env_mask_dev is NULL); refreshes obs like get_observations() at reset (lidar part = 1.0). */
+int isx_reset(isx_handle *h, const uint8_t *env_mask_dev, void *stream);
+
+/* step(throttles, steerings, dt)  (IntersectionEnv.cpp:133-392, bindings.cpp:76).
+ * actions_dev = [E][N][2] f32 (throttle, steer).  Results land in the isx_buffers views. */
+int isx_step(isx_handle *h, const float *actions_dev, float dt, void *stream);
+
+/* Same call with HOST buffers (what env.py does around env.step, env.py:167-208): copies actions in,
+ * steps, copies obs / reward / done / status / terminated / truncated out and synchronises.
+ * Any output pointer may be NULL. */
+int isx_step_host(isx_handle *h, const float *actions, float dt, float *obs, float *reward, uint8_t *done,
+                  uint8_t *status, uint8_t *terminated, uint8_t *truncated, void *stream);
+
+/* `steps` consecutive steps with actions drawn on the device from the Philox action stream
+ * (DESIGN.md "RNG streams"); with auto_reset this is the random-action rollout BASELINE.json quotes. */
+int isx_rollout(isx_handle *h, int32_t steps, float dt, void *stream);
+
+int isx_get_buffers(isx_handle *h, isx_buffers *out);
+int isx_num_envs(isx_handle *h);
+int isx_num_agents(isx_handle *h);
+
+/* Snapshot / injection of one env (get_state / set_state, IntersectionEnv.cpp:394-416, EnvState.h:9-15).
+ * Synchronous.  egos: N records; npcs: up to cap records, *n_npcs = live count. */
+int isx_get_env_state(isx_handle *h, int32_t env, isx_car_state *egos, isx_car_state *npcs, int32_t cap,
+                      int32_t *n_npcs, int32_t *step_count, uint32_t *tick);
+int isx_set_env_state(isx_handle *h, int32_t env, const isx_car_state *egos, const isx_car_state *npcs,
+                      int32_t n_npcs, int32_t step_count, uint32_t tick);
+/* get_observations() (IntersectionEnv.cpp:418-520) for the current state, without stepping. */
+int isx_observe(isx_handle *h, void *stream);
+
+int isx_stats_read(isx_handle *h, isx_stats *out);     /* synchronous */
+int isx_stats_reset(isx_handle *h);
+/* device pointer to the raw counters (int64[16], reward_sum as double in slot 15) for an NCCL all-reduce */
+int isx_stats_device_ptr(isx_handle *h, void **ptr, int32_t *n_int64);
+
+/* Host-side route table probe (RouteGen.cpp:7-205 restated in the library): returns the path length,
+ * ISX_E_ROUTE_START / ISX_E_ROUTE_END for unknown ids.  path_xy = 320 floats. */
+int isx_route(int32_t num_lanes, const char *start_id, const char *end_id, float *path_xy, int32_t *intent,
+              float *spawn_x, float *spawn_y, float *spawn_heading);
+
+/* Device self-test of the restated libm (csrc/isx_math.cuh): evaluates sincosf/tanf/atan2f/hypotf/wrap on
+ * n host-supplied inputs ON THE GPU and returns the results, so tests can compare with the host libm. */
+int isx_math_probe(int32_t device, int32_t n, const float *a, const float *b, float *sin_a, float *cos_a,
+                   float *tan_a, float *atan2_ab, float *hypot_ab, float *wrap_a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISX_H */

@@ -1,0 +1,111 @@
+// isx_host_units.cpp — HOST build of the entity-level product arithmetic (isx_sim.cuh, isx_tables.h,
+// isx_rng.cuh) behind a C ABI.  Test hook only (tests/test_host_units.py compares it with the reference
+// build and the oracle on the CPU, where iteration is cheap); the product path never loads this library
+// and has no CPU fallback.  Built with g++ -O2 -ffp-contract=off, no -march.
+#include "isx_rng.cuh"
+#include "isx_sim.cuh"
+#include "isx_tables.h"
+
+#include <map>
+#include <mutex>
+
+using namespace isx;
+
+namespace {
+std::mutex g_mu;
+std::map<int, RoadTables*> g_tables;
+const RoadTables* tables_for(int lanes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_tables.find(lanes);
+    if (it == g_tables.end()) {
+        RoadTables* t = new RoadTables();
+        if (!build_road_tables(lanes, t)) { std::fprintf(stderr, "road map not symmetric\n"); std::abort(); }
+        it = g_tables.emplace(lanes, t).first;
+    }
+    return it->second;
+}
+}  // namespace
+
+extern "C" {
+
+int isxh_route(int lanes, const char* start, const char* end, float* path_xy, int* intent, float* sx, float* sy, float* sh) {
+    RouteHost r;
+    const int rc = build_route(lanes, start, end, &r);
+    if (rc) return rc;
+    for (int i = 0; i < PATH_LEN; ++i) { path_xy[2 * i] = r.path[i].x; path_xy[2 * i + 1] = r.path[i].y; }
+    *intent = r.intent; *sx = r.spawn_x; *sy = r.spawn_y; *sh = r.spawn_h;
+    return PATH_LEN;
+}
+int isxh_on_road(int lanes, float x, float y) { return on_road(lanes, x, y) ? 1 : 0; }
+int isxh_yellow(int lanes, float x, float y) { return hits_yellow(lanes, x, y) ? 1 : 0; }
+int isxh_is_line(int lanes, int x, int y) { return is_line_px(lanes, x, y) ? 1 : 0; }
+// unfolded views of the folded tables, for exhaustive comparison with the reference maps
+void isxh_road_map(int lanes, uint8_t* out) {
+    const RoadTables* t = tables_for(lanes);
+    for (int y = 0; y < HEIGHT; ++y) for (int x = 0; x < WIDTH; ++x) out[y * WIDTH + x] = road_bit(t->bits.data(), x, y) ? 1 : 0;
+}
+void isxh_line_map(int lanes, uint8_t* out) {
+    for (int y = 0; y < HEIGHT; ++y) for (int x = 0; x < WIDTH; ++x) out[y * WIDTH + x] = is_line_px(lanes, x, y) ? 1 : 0;
+}
+void isxh_skip_map(int lanes, uint8_t* out) {
+    const RoadTables* t = tables_for(lanes);
+    for (int y = 0; y < HEIGHT; ++y) for (int x = 0; x < WIDTH; ++x) out[y * WIDTH + x] = (uint8_t)road_skip(t->skip.data(), x, y);
+}
+void isxh_car_update(float* s, float thr, float st, float dt) {
+    Pose p{s[0], s[1], s[2], s[3]};
+    float acc = s[4], steer = s[5];
+    car_update(p, steer, acc, thr, st, dt);
+    s[0] = p.x; s[1] = p.y; s[2] = p.v; s[3] = p.h; s[4] = acc; s[5] = steer;
+}
+int isxh_collide(const float* a, const float* b) { return cars_collide(a[0], a[1], a[2], b[0], b[1], b[2]) ? 1 : 0; }
+void isxh_corners(const float* a, float* out8) {
+    float s, c, cx[4], cy[4];
+    sincosf_(a[2], &s, &c);
+    car_corners(a[0], a[1], s, c, cx, cy);
+    for (int i = 0; i < 4; ++i) { out8[2 * i] = cx[i]; out8[2 * i + 1] = cy[i]; }
+}
+// The product lidar for one ego: road sphere-trace + per-car slab/verify, as the kernel evaluates it.
+void isxh_lidar(int lanes, int rays, const float* self_pose, const float* others, int n_others, float* dist) {
+    const RoadTables* t = tables_for(lanes);
+    std::vector<float> rel((size_t)rays);
+    lidar_rel_angles(rays, rel.data());
+    const float cx = self_pose[0], cy = self_pose[1], h = self_pose[2];
+    std::vector<PixRect> rects;
+    for (int i = 0; i < n_others; ++i) {
+        const float ox = others[3 * i], oy = others[3 * i + 1], oh = others[3 * i + 2];
+        if (fabsf(ox - cx) < 1e-3f && fabsf(oy - cy) < 1e-3f && fabsf(oh - h) < 1e-3f) continue;   // Lidar.cpp:58-63
+        rects.push_back(car_pixel_rect(ox, oy, oh));
+    }
+    for (int i = 0; i < rays; ++i) {
+        float s, c;
+        sincosf_(h + rel[i], &s, &c);
+        const float dx = c, dy = -s;
+        bool hit;
+        const int ke = ray_road_event(t->bits.data(), t->skip.data(), cx, cy, dx, dy, &hit);
+        int best = hit ? ke : 0;
+        const int kmax = hit ? ke - 1 : ke - 1;     // cars only count strictly before the road event
+        if (kmax >= 1) {
+            for (const PixRect& r : rects) {
+                const int lim = best ? best - 1 : kmax;
+                if (lim < 1) break;
+                const int k = ray_rect_first_hit(r, cx, cy, dx, dy, lim);
+                if (k) best = k;
+            }
+        }
+        dist[i] = best ? (float)(4 * best) : LIDAR_MAX_DIST;
+    }
+}
+int isxh_self_status(int lanes, float x, float y, float h, float gx, float gy, float px, float py) {
+    return ego_self_status(lanes, x, y, h, F2{gx, gy}, F2{px, py});
+}
+void isxh_actions(uint64_t seed, uint32_t env, uint32_t tick, int n, float* out) {
+    for (int a = 0; a < n; ++a) philox_action(seed, env, tick, (uint32_t)a, out[2 * a], out[2 * a + 1]);
+}
+// first `n` words of a traffic stream + the u01 / below(12) views of a fresh stream
+void isxh_traffic_words(uint64_t seed, uint32_t env, uint32_t tick, int n, uint32_t* out) {
+    TrafficStream s; s.init(seed, env, tick);
+    for (int i = 0; i < n; ++i) out[i] = s.next();
+}
+float isxh_u01_of(uint64_t seed, uint32_t env, uint32_t tick) { TrafficStream s; s.init(seed, env, tick); return s.uniform01(); }
+
+}  // extern "C"

@@ -26,8 +26,10 @@
 
 #if defined(__CUDACC__)
 #define ISX_HD __host__ __device__ __forceinline__
+#define ISX_HDM __host__ __device__ __forceinline__     // member functions
 #else
 #define ISX_HD static inline
+#define ISX_HDM inline
 #endif
 
 namespace isx {

@@ -1,0 +1,420 @@
+// isx_sim.cuh — entity-level simulation arithmetic, __host__ __device__.
+//
+// Every function here is the float32 arithmetic of one reference function, written so that the SAME
+// sequence of IEEE operations happens (no contraction: build with -fmad=false / -ffp-contract=off) and
+// with the libm calls replaced by the bit-identical restatements of isx_math.cuh.  The kernels
+// (isx_kernels.cu) decide which thread evaluates what; nothing here knows about warps.
+// The host build is exercised against the reference in tests/test_host_units.py.
+#pragma once
+#include "isx_math.cuh"
+
+namespace isx {
+
+// constants.h:4-20
+constexpr int WIDTH = 750;
+constexpr int HEIGHT = 750;
+constexpr float CAR_LENGTH = 54.0f;
+constexpr float CAR_WIDTH = 24.0f;
+constexpr float LANE_WIDTH_PX = 42.0f;
+constexpr float CORNER_RADIUS = 84.0f;
+constexpr float MAX_ACC = 15.0f;
+constexpr float MAX_STEERING_ANGLE = 0.6108652381980153f;
+constexpr float PHYSICS_MAX_SPEED = 8.0f;
+constexpr float FPS = 60.0f;
+constexpr float SCALE = 12.0f;
+constexpr int PATH_LEN = 160;
+constexpr int LIDAR_MAX_K = 62;          // samples at 4,8,...,248 px (Lidar.cpp:33: dist < 250)
+constexpr float LIDAR_STEP = 4.0f;
+constexpr float LIDAR_MAX_DIST = 250.0f;
+
+struct Pose { float x, y, v, h; };
+struct alignas(8) F2 { float x, y; };   // way-point / goal (8-byte vector load on the device)
+
+// ---------------------------------------------------------------- road geometry
+// RoadGeometry::is_on_road (RoadGeometry.h:19-58): (two strips U four corner squares) \ four grass discs.
+ISX_HD bool on_road(int lanes, float x, float y) {
+    const float C = WIDTH * 0.5f;
+    const float rw = (float)lanes * LANE_WIDTH_PX;
+    const float cr = CORNER_RADIUS;
+    const float lo = C - rw - cr, hi = C + rw + cr;     // grass-disc centres, also outer edge of the squares
+    const float r2 = cr * cr;
+    const float dxl = x - lo, dxh = x - hi, dyl = y - lo, dyh = y - hi;
+    if (dxl * dxl + dyl * dyl <= r2) return false;
+    if (dxh * dxh + dyl * dyl <= r2) return false;
+    if (dxl * dxl + dyh * dyh <= r2) return false;
+    if (dxh * dxh + dyh * dyh <= r2) return false;
+    const float a = C - rw, b = C + rw;
+    const bool in_v = (x >= a) && (x <= b);
+    const bool in_h = (y >= a) && (y <= b);
+    if (in_v || in_h) return true;
+    const bool xl = (x >= lo) && (x <= a), xr = (x >= b) && (x <= hi);
+    const bool yt = (y >= lo) && (y <= a), yb = (y >= b) && (y <= hi);
+    return (xl || xr) && (yt || yb);
+}
+
+// RoadGeometry::hits_yellow_line (RoadGeometry.h:60-67)
+ISX_HD bool hits_yellow(int lanes, float x, float y) {
+    const float C = WIDTH * 0.5f;
+    const float rw = (float)lanes * LANE_WIDTH_PX;
+    const float ax = fabsf(x - C), ay = fabsf(y - C);
+    return (ax <= 2.0f && ay > rw) || (ay <= 2.0f && ax > rw);
+}
+
+// LineMask (LineMask.cpp:47-72, LineMask.h:15-18) in closed form: double lines at 373/377 +-1 px, drawn
+// from each screen edge to the stop line at centre -+ (lanes*42 + 84).
+ISX_HD bool is_line_px(int lanes, int x, int y) {
+    if ((unsigned)x >= (unsigned)WIDTH || (unsigned)y >= (unsigned)HEIGHT) return false;
+    const int c = WIDTH / 2;
+    const int stop = lanes * (int)LANE_WIDTH_PX + (int)CORNER_RADIUS;
+    const int ux = x - c, uy = y - c;
+    const int ax = ux < 0 ? -ux : ux, ay = uy < 0 ? -uy : uy;
+    const bool band_x = (ax >= 1 && ax <= 3);      // columns 372..374, 376..378
+    const bool band_y = (ay >= 1 && ay <= 3);
+    const bool far_y = (uy <= -stop) || (uy >= stop);
+    const bool far_x = (ux <= -stop) || (ux >= stop);
+    return (band_x && far_y) || (band_y && far_x);
+}
+
+// ---------------------------------------------------------------- car
+// Car::update (Car.cpp:9-40).  Kinematic bicycle; NOTE the pose step has no dt (px per frame).
+ISX_HD void car_update(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt) {
+    acc = throttle * MAX_ACC;
+    const float target = steer_in * MAX_STEERING_ANGLE;
+    steer = steer + (target - steer) * 0.2f;
+    float v = p.v;
+    if (throttle == 0.0f) v = v * 0.95f;
+    v = v + acc * dt;
+    if (v < 0.0f) v = 0.0f;
+    if (v > PHYSICS_MAX_SPEED) v = PHYSICS_MAX_SPEED;
+    float h = p.h;
+    if (fabsf(v) > 0.1f) {
+        const float yaw = (v / CAR_LENGTH) * tanf_(steer);
+        h = h + yaw;
+    }
+    h = fmodf_(h + PI_F, TWO_PI_F);
+    if (h < 0.0f) h = h + TWO_PI_F;
+    h = h - PI_F;
+    float s, c;
+    sincosf_(h, &s, &c);
+    p.x = p.x + v * c;
+    p.y = p.y - v * s;
+    p.v = v;
+    p.h = h;
+}
+
+// Car::corners (Car.cpp:86-103): (+-27, +-12) rotated by +heading (no y flip) — order FL, FR, RR, RL.
+ISX_HD void car_corners(float x, float y, float s, float c, float cx[4], float cy[4]) {
+    const float hl = CAR_LENGTH * 0.5f, hw = CAR_WIDTH * 0.5f;
+    cx[0] = x + hl * c - hw * s;        cy[0] = y + hl * s + hw * c;
+    cx[1] = x + hl * c - (-hw) * s;     cy[1] = y + hl * s + (-hw) * c;
+    cx[2] = x + (-hl) * c - (-hw) * s;  cy[2] = y + (-hl) * s + (-hw) * c;
+    cx[3] = x + (-hl) * c - hw * s;     cy[3] = y + (-hl) * s + hw * c;
+}
+
+// Car::check_collision (Car.cpp:105-141): separating-axis test over the 2+2 edge directions, touching = hit.
+ISX_HD bool sat_overlap(const float ax[4], const float ay[4], float as, float ac,
+                        const float bx[4], const float by[4], float bs, float bc) {
+    const float ux[4] = {ac, -as, bc, -bs};
+    const float uy[4] = {as, ac, bs, bc};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float lo1 = ax[0] * ux[k] + ay[0] * uy[k], hi1 = lo1;
+        float lo2 = bx[0] * ux[k] + by[0] * uy[k], hi2 = lo2;
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+            const float p = ax[i] * ux[k] + ay[i] * uy[k];
+            lo1 = fminf(lo1, p); hi1 = fmaxf(hi1, p);
+            const float q = bx[i] * ux[k] + by[i] * uy[k];
+            lo2 = fminf(lo2, q); hi2 = fmaxf(hi2, q);
+        }
+        if (hi1 < lo2 || hi2 < lo1) return false;
+    }
+    return true;
+}
+
+// Conservative reject before the SAT: two 54x24 rectangles whose centres are > 70 px apart are
+// separated by > 10 px, and then one of the four SAT axes shows a gap of > 7 px — far above float
+// rounding — so the exact SAT would also answer "no".  Exactness-preserving by construction.
+ISX_HD bool cars_far_apart(float x1, float y1, float x2, float y2) {
+    const float dx = x1 - x2, dy = y1 - y2;
+    return dx * dx + dy * dy > 4900.0f;
+}
+
+ISX_HD bool cars_collide(float x1, float y1, float h1, float x2, float y2, float h2) {
+    if (cars_far_apart(x1, y1, x2, y2)) return false;
+    float s1, c1, s2, c2;
+    sincosf_(h1, &s1, &c1);
+    sincosf_(h2, &s2, &c2);
+    float ax[4], ay[4], bx[4], by[4];
+    car_corners(x1, y1, s1, c1, ax, ay);
+    car_corners(x2, y2, s2, c2, bx, by);
+    return sat_overlap(ax, ay, s1, c1, bx, by, s2, c2);
+}
+
+// Car::update_path_index (Car.cpp:47-74): first minimum of squared distance over path[idx, idx+50).
+ISX_HD int path_index_update(const F2* path, int idx, float x, float y) {
+    int start = idx < 0 ? 0 : idx;
+    int end = start + 50;
+    if (end > PATH_LEN) end = PATH_LEN;
+    float best = INFINITY;
+    int bi = start;
+    for (int i = start; i < end; ++i) {
+        const F2 p = path[i];
+        const float dx = p.x - x, dy = p.y - y;
+        const float d = dx * dx + dy * dy;
+        if (d < best) { best = d; bi = i; }
+    }
+    return bi;
+}
+
+// ---------------------------------------------------------------- ego status (IntersectionEnv.cpp:166-290)
+// goal = path[159], prev = path[158].  Returns ISX status code of the car on its own (before car-car).
+ISX_HD int ego_self_status(int lanes, float x, float y, float h, F2 goal, F2 prev) {
+    const float dxr = goal.x - prev.x, dyr = goal.y - prev.y;
+    bool ok;
+    if (fabsf(dxr) > fabsf(dyr)) ok = (fabsf(y - goal.y) < 15.0f) && (fabsf(x - goal.x) < 40.0f);
+    else                         ok = (fabsf(x - goal.x) < 15.0f) && (fabsf(y - goal.y) < 40.0f);
+    if (ok) return 2;  // SUCCESS
+    float s, c, cx[4], cy[4];
+    sincosf_(h, &s, &c);
+    car_corners(x, y, s, c, cx, cy);
+    const float lo = -100.0f, hi = (float)WIDTH + 100.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (cx[k] < lo || cx[k] > hi || cy[k] < lo || cy[k] > hi) return 3;  // CRASH_WALL (left the screen)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (!on_road(lanes, cx[k], cy[k])) return 3;                          // CRASH_WALL (off road)
+    bool line = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) line = line || hits_yellow(lanes, cx[k], cy[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int k2 = (k + 1) & 3;
+        const float mx = 0.5f * (cx[k] + cx[k2]), my = 0.5f * (cy[k] + cy[k2]);
+        line = line || is_line_px(lanes, f2i_rz(mx), f2i_rz(my));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) line = line || is_line_px(lanes, f2i_rz(cx[k]), f2i_rz(cy[k]));
+    return line ? 4 : 0;  // CRASH_LINE / ALIVE
+}
+
+// ---------------------------------------------------------------- reward pieces (IntersectionEnv.cpp:15-46)
+struct RewardCfg { float k_prog, v_min_ms, k_stuck, k_cv, k_co, k_succ, k_sm, alpha; };
+
+ISX_HD float reward_base(const RewardCfg& rc, float x, float y, float v, float acc, float steer, F2 goal,
+                         float max_progress, float& prev_dist, float& pa0, float& pa1) {
+    const float cur = hypotf_(x - goal.x, y - goal.y);
+    float r_prog = 0.0f;
+    if (prev_dist > 0.0f) {
+        const float progress = prev_dist - cur;
+        const float norm = (max_progress > 0.0f) ? (progress / max_progress) : 0.0f;
+        r_prog = rc.k_prog * norm;
+    }
+    prev_dist = cur;
+    const float speed_ms = (v * FPS) / SCALE;
+    const float r_stuck = (speed_ms < rc.v_min_ms) ? rc.k_stuck : 0.0f;
+    const float an = acc / MAX_ACC, sn = steer / MAX_STEERING_ANGLE;
+    const float d0 = an - pa0, d1 = sn - pa1;
+    const float r_smooth = rc.k_sm * (d0 * d0 + d1 * d1);
+    pa0 = an; pa1 = sn;
+    return r_prog + r_stuck + r_smooth;
+}
+
+// ---------------------------------------------------------------- lidar (Lidar.cpp:16-90)
+// Integer pixel rectangle equivalent to the float AABB test of Lidar.cpp:65-78:
+//   float(px) >= c.x - ex  &&  float(px) <= c.x + ex   <=>   ceil(c.x - ex) <= px <= floor(c.x + ex)
+struct PixRect { int x0, x1, y0, y1; };
+ISX_HD PixRect car_pixel_rect(float x, float y, float h) {
+    float s, c;
+    sincosf_(h, &s, &c);
+    const float hl = CAR_LENGTH * 0.5f, hw = CAR_WIDTH * 0.5f;
+    const float ex = fabsf(c) * hl + fabsf(s) * hw;
+    const float ey = fabsf(s) * hl + fabsf(c) * hw;
+    PixRect r;
+    r.x0 = (int)ceilf(x - ex); r.x1 = (int)floorf(x + ex);
+    r.y0 = (int)ceilf(y - ey); r.y1 = (int)floorf(y + ey);
+    return r;
+}
+
+// Pixel of sample k on a ray (Lidar.cpp:34-35): mul and add rounded separately, truncation toward 0.
+ISX_HD void ray_pixel(float cx, float cy, float dx, float dy, int k, int& px, int& py) {
+    const float dist = (float)(4 * k);
+    px = f2i_rz(cx + dx * dist);
+    py = f2i_rz(cy + dy * dist);
+}
+
+// Folded road tables (built on the host from on_road(), see isx_tables.cpp):
+//   bits : (HALF+1) rows x ROAD_WORDS u32, bit (u,v) = on_road(375+-u, 375+-v)  (the map is mirror-symmetric)
+//   skip : (SKIP_DIM x SKIP_DIM) u8 per 4x4 block of (u,v): samples that can be skipped for sure
+constexpr int ROAD_HALF = 375;               // u,v in [0,375]
+constexpr int ROAD_WORDS = 13;               // 376 bits -> 12 words, padded to an odd stride against bank conflicts
+constexpr int ROAD_ROWS = ROAD_HALF + 1;
+constexpr int SKIP_DIM = 94;                 // ceil(376/4)
+
+ISX_HD bool road_bit(const uint32_t* bits, int px, int py) {
+    int u = px - ROAD_HALF; u = u < 0 ? -u : u;
+    int v = py - ROAD_HALF; v = v < 0 ? -v : v;
+    return (bits[v * ROAD_WORDS + (u >> 5)] >> (u & 31)) & 1u;
+}
+ISX_HD int road_skip(const uint8_t* skip, int px, int py) {
+    int u = px - ROAD_HALF; u = u < 0 ? -u : u;
+    int v = py - ROAD_HALF; v = v < 0 ? -v : v;
+    return skip[(v >> 2) * SKIP_DIM + (u >> 2)];
+}
+
+// First road event on a ray: returns k in [1,62] and sets *hit (true = off-road pixel, false = left the
+// screen), or 63 if nothing happens within range.  k = 0 means the origin pixel itself is off screen
+// (Lidar.cpp:38-40 breaks at dist 0).  Sphere-traces with the skip table: a sample whose 4x4 block has
+// skip count j guarantees that the next j samples are on-road and on-screen, so they are not evaluated.
+ISX_HD int ray_road_event(const uint32_t* bits, const uint8_t* skip, float cx, float cy, float dx, float dy, bool* hit) {
+    int px, py;
+    *hit = false;
+    ray_pixel(cx, cy, dx, dy, 0, px, py);
+    if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return 0;
+    int k = 0;
+    while (true) {
+        k += road_skip(skip, px, py) + 1;
+        if (k > LIDAR_MAX_K) return LIDAR_MAX_K + 1;
+        ray_pixel(cx, cy, dx, dy, k, px, py);
+        if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return k;
+        if (!road_bit(bits, px, py)) { *hit = true; return k; }
+    }
+}
+
+// First sample k in [1, kmax] whose pixel lies inside the rectangle, or 0.  A slab test in real arithmetic
+// (0.01 px slack, >100x the float rounding of the sample positions) brackets the candidate k range; the
+// candidates are then checked with the exact integer test, in order.  Only on-screen pixels can be hit
+// (the march breaks off screen first), so the rectangle is clamped to the screen; truncation toward zero
+// maps every value in (-1, 1) to pixel 0, hence the wider lower bound when the clamped edge is 0.
+ISX_HD int ray_rect_first_hit(const PixRect& r, float cx, float cy, float dx, float dy, int kmax) {
+    const int x0 = r.x0 < 0 ? 0 : r.x0, x1 = r.x1 > WIDTH - 1 ? WIDTH - 1 : r.x1;
+    const int y0 = r.y0 < 0 ? 0 : r.y0, y1 = r.y1 > HEIGHT - 1 ? HEIGHT - 1 : r.y1;
+    if (x0 > x1 || y0 > y1) return 0;
+    float t0 = 0.0f, t1 = (float)(4 * kmax) + 0.5f;
+    {
+        const float lo = (x0 == 0 ? -1.01f : (float)x0 - 0.01f) - cx, hi = ((float)x1 + 1.01f) - cx;
+        if (fabsf(dx) > 1e-6f) {
+            const float inv = 1.0f / dx;
+            float a = lo * inv, b = hi * inv;
+            if (a > b) { const float t = a; a = b; b = t; }
+            t0 = fmaxf(t0, a); t1 = fminf(t1, b);
+        } else if (lo > 0.01f || hi < -0.01f) return 0;
+    }
+    {
+        const float lo = (y0 == 0 ? -1.01f : (float)y0 - 0.01f) - cy, hi = ((float)y1 + 1.01f) - cy;
+        if (fabsf(dy) > 1e-6f) {
+            const float inv = 1.0f / dy;
+            float a = lo * inv, b = hi * inv;
+            if (a > b) { const float t = a; a = b; b = t; }
+            t0 = fmaxf(t0, a); t1 = fminf(t1, b);
+        } else if (lo > 0.01f || hi < -0.01f) return 0;
+    }
+    if (!(t0 <= t1)) return 0;
+    int ka = (int)floorf(t0 * 0.25f - 0.01f);      // one early is harmless: candidates are verified
+    int kb = (int)ceilf(t1 * 0.25f + 0.01f);
+    if (ka < 1) ka = 1;
+    if (kb > kmax) kb = kmax;
+    for (int k = ka; k <= kb; ++k) {
+        int px, py;
+        ray_pixel(cx, cy, dx, dy, k, px, py);
+        if (px >= x0 && px <= x1 && py >= y0 && py <= y1) return k;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- NPC planner pieces (TrafficFlow.cpp:22-196)
+// Pairwise, ghost-index-independent part of the yield logic for NPC `me` against NPC `ot`:
+//   bit0 : `ot` can conflict at all (not same-direction < 60 deg :103-104, not a stable side-by-side car :107-159)
+//   bit1 : yield rules 2-4 hold (:167-176); rule 1 (dist_to_crash < 15) depends on the ghost point.
+ISX_HD int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, float me_cos, float me_dc, bool me_before_ot) {
+    const float ad = fabsf(wrap_angle(me.h - ot.h));
+    if (ad < (60.0f * PI_F / 180.0f)) return 0;
+    const float dxt = ot.x - me.x, dyt = ot.y - me.y;
+    const float dto = hypotf_(dxt, dyt);
+    if (dto > 1e-5f) {
+        const float mx = me_cos, my = -me_sin;
+        const float adn = fminf(ad, 2.0f * PI_F - ad);
+        const bool parallel = (adn < (30.0f * PI_F / 180.0f)) || (adn > (150.0f * PI_F / 180.0f));
+        if (parallel) {
+            const float lon = dxt * mx + dyt * my;
+            const float lat = fsqrt_rn(fmaxf(0.0f, dto * dto - lon * lon));
+            if (fabsf(lat) < (LANE_WIDTH_PX * 1.5f) && fabsf(lon) < (CAR_LENGTH * 2.0f)) {
+                const float fd = 20.0f;
+                const float mfx = me.x + mx * fd, mfy = me.y + my * fd;
+                float so, co;
+                sincosf_(ot.h, &so, &co);
+                const float ofx = ot.x + co * fd, ofy = ot.y + (-so) * fd;
+                const float fdx = ofx - mfx, fdy = ofy - mfy;
+                const float fmag = hypotf_(fdx, fdy);
+                if (fmag > 1e-5f) {
+                    const float flon = fdx * mx + fdy * my;
+                    const float flat = fsqrt_rn(fmaxf(0.0f, fmag * fmag - flon * flon));
+                    if (fabsf(flat - lat) < (LANE_WIDTH_PX * 0.5f)) return 0;
+                }
+            }
+        }
+    }
+    const float ot_dc = hypotf_(ot.x - WIDTH * 0.5f, ot.y - HEIGHT * 0.5f);
+    bool y = false;
+    if (me.v < 1.0f && ot.v > 3.0f && ot_dc < me_dc + 25.0f) y = true;
+    else if (ot_dc < me_dc - 5.0f) y = true;
+    else if (fabsf(ot_dc - me_dc) <= 5.0f) y = me_before_ot;
+    return 1 | (y ? 2 : 0);
+}
+
+// get_front_car_dist_tf contribution of one other NPC (TrafficFlow.cpp:28-44): its distance, or 1e9.
+ISX_HD float npc_front_candidate(const Pose& me, const Pose& ot, float me_sin, float me_cos) {
+    const float dx = ot.x - me.x, dy = ot.y - me.y;
+    const float d = hypotf_(dx, dy);
+    if (d > 80.0f) return 1e9f;
+    const float vx = me_cos, vy = -me_sin;
+    const float dot = (dx * vx + dy * vy) / (d + 1e-5f);
+    if (dot > 0.8f) {
+        const float ad = fabsf(wrap_angle(me.h - ot.h));
+        if (ad < (45.0f * PI_F / 180.0f)) return d;
+    }
+    return 1e9f;
+}
+
+// Lateral P-control + cruise thresholds + front-car braking (TrafficFlow.cpp:50-75).
+ISX_HD float npc_steer_cmd(const Pose& me, F2 target) {
+    const float dx = target.x - me.x, dy = target.y - me.y;
+    const float err = wrap_angle(atan2f_(-dy, dx) - me.h);
+    return fmaxf(-1.0f, fminf(1.0f, err * 3.0f));
+}
+ISX_HD float npc_cruise_throttle(float v, float front_dist) {
+    const float target = PHYSICS_MAX_SPEED * 0.4f;
+    float thr = 0.0f;
+    if (v < target) thr = 0.5f;
+    else if (v > target + 1.0f) thr = -0.1f;
+    if (front_dist < 30.0f) thr = -1.0f;
+    else if (front_dist < 50.0f) thr = fminf(thr, -0.2f);
+    return thr;
+}
+ISX_HD float npc_final_throttle(float thr, bool conflict, float min_conflict_dist) {
+    if (!conflict) return thr;
+    if (min_conflict_dist < 35.0f) return -1.0f;
+    if (min_conflict_dist < 60.0f) return -0.8f;
+    return fminf(thr, 0.0f);
+}
+
+// ---------------------------------------------------------------- observation pieces (IntersectionEnv.cpp:431-458, 494-507)
+ISX_HD void obs_ego_features(const Pose& p, F2 target, float* o6) {
+    o6[0] = p.x / (float)WIDTH;
+    o6[1] = p.y / (float)HEIGHT;
+    o6[2] = p.v / PHYSICS_MAX_SPEED;
+    o6[3] = p.h / PI_F;
+    const float dx = target.x - p.x, dy = target.y - p.y;
+    o6[4] = fsqrt_rn(dx * dx + dy * dy) / (float)WIDTH;
+    o6[5] = wrap_angle(atan2f_(-dy, dx) - p.h) / PI_F;
+}
+ISX_HD void obs_neighbor_features(const Pose& me, const Pose& ot, int intent, float* o5) {
+    o5[0] = (ot.x - me.x) / (float)WIDTH;
+    o5[1] = (ot.y - me.y) / (float)HEIGHT;
+    o5[2] = (ot.v - me.v) / PHYSICS_MAX_SPEED;
+    o5[3] = wrap_angle(ot.h - me.h) / PI_F;
+    o5[4] = (float)intent;
+}
+
+}  // namespace isx

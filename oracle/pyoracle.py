@@ -93,7 +93,16 @@ def _load(path: str, prefix: str):
     if key in _libs:
         return _libs[key]
     lib = C.CDLL(path)
-    f = lambda n: getattr(lib, prefix + n)
+
+    class _Missing:  # a library may export only a subset (the product's host-unit hooks do)
+        restype = None
+        argtypes = None
+
+    def f(n):
+        try:
+            return getattr(lib, prefix + n)
+        except AttributeError:
+            return _Missing()
     f("create").restype = C.c_void_p
     f("create").argtypes = [C.c_int]
     f("destroy").argtypes = [C.c_void_p]
@@ -368,6 +377,11 @@ class RefEnv(_EnvBase):
 class OracleEnv(_EnvBase):
     _so = ORACLE_SO
     _prefix = "isxo_"
+
+
+def unit_of(path: str, prefix: str) -> _Unit:
+    """Unit-probe view of any library exporting the <prefix>route / on_road / lidar ... subset."""
+    return _Unit(_load(path, prefix), prefix)
 
 
 def ref_unit() -> _Unit:
