@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the batched intersection stepper on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[4], the configuration the 1e9 target is quoted on): 8 agents per env + NPC traffic
+density 1.0, 72-beam lidar, 3 lanes, random actions from the on-device Philox stream, respawn on, max_steps 2000,
+auto-reset.  Each GPU owns 8192 env instances (65,536 envs over 8 GPUs) -> weak scaling, no per-step collective;
+the only collective is one NCCL all-reduce of the episode counters after the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              # native arm (CUDA, this repo)
+  python bench.py --impl reference [--gpus N] [--steps K] ...       # the reference's own CPU env on the host cores
+
+One JSON line on stdout (rank 0).  See the module-level comments next to each key for what is measured.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "agent_steps_per_sec"
+UNIT = "agent-steps/s"
+ALGO_BYTES_PER_AGENT_STEP = 610  # 8 action + 2x40 ego state + 8 consts + 508 obs + 4 reward + 1 done + 1 status
+ENVS_PER_GPU = 8192
+N_AGENTS = 8
+DT = 1.0 / 60.0
+
+ROUTES8 = [("IN_1", "OUT_4"), ("IN_2", "OUT_8"), ("IN_3", "OUT_12"), ("IN_4", "OUT_7"),
+           ("IN_5", "OUT_11"), ("IN_6", "OUT_3"), ("IN_7", "OUT_10"), ("IN_8", "OUT_2")]
+
+
+def workload_config(n_gpus, envs_per_gpu):
+    return {
+        "workload": "C5: 8 agents/env + NPC traffic density 1.0, 72-beam lidar, 3 lanes, random Philox actions, respawn, "
+                    "max_steps 2000, auto-reset",
+        "envs_per_gpu": envs_per_gpu, "agents_per_env": N_AGENTS, "global_envs": envs_per_gpu * n_gpus,
+        "lidar_rays": 72, "traffic_density": 1.0, "dt": DT, "parallelism": f"env-shard x{n_gpus} (no per-step collective)",
+        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
+    }
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_run(samples: int, warmup: int, steps_per_sample: int, threads: int):
+    """Times the reference's own CPU implementation (oracle/_ref, the unmodified C++ behind a C ABI) — or the C port
+    when _ref did not travel — with one env per host thread on the bench workload.  Returns (value, info)."""
+    import pyoracle as po
+
+    kind = "reference" if po.have_ref() else "port"
+    cls = po.RefEnv if kind == "reference" else po.OracleEnv
+    envs = [cls(num_lanes=3, ego_routes=ROUTES8, traffic=True, density=1.0, lidar_rays=72, seed=0, env_id=i, max_steps=2000)
+            for i in range(threads)]
+    done_steps = [0] * threads
+
+    def work(i, n):
+        a, _, _ = envs[i].rollout(n, DT)
+        done_steps[i] = a
+
+    def one_sample(n):
+        ts = [threading.Thread(target=work, args=(i, n)) for i in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0, sum(done_steps)
+
+    for _ in range(warmup):
+        one_sample(steps_per_sample)
+    tot_t, tot_a = 0.0, 0
+    for _ in range(samples):
+        dt_, a = one_sample(steps_per_sample)
+        tot_t += dt_
+        tot_a += a
+    info = {"kind": kind, "cores": threads,
+            "sample": f"{threads} envs (one per host thread) x {steps_per_sample} env-steps x {samples} samples of the bench workload"}
+    return tot_a / tot_t, tot_t / max(samples, 1), info
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu = gpu_index
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    K, W = max(1, args.steps), max(3, args.warmup)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        value, s_per_step, info = cpu_reference_run(samples=K, warmup=min(W, 3), steps_per_sample=25, threads=threads)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+                "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(n_gpus, args.envs_per_gpu),
+                "cpu_baseline": dict(info, value=value, unit=UNIT),
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from marl_traffic_intersection_b200 import BatchedIntersectionEnv
+
+    E = args.envs_per_gpu
+    env = BatchedIntersectionEnv({
+        "num_envs": E, "num_agents": N_AGENTS, "num_lanes": 3, "ego_routes": ROUTES8, "traffic_flow": True, "traffic_density": 1.0,
+        "lidar_rays": 72, "respawn_enabled": True, "max_steps": 2000, "auto_reset": True, "seed": 0, "env_id_base": rank * E,
+        "npc_capacity": 16, "device": dev,
+    })
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- warm-up
+    env.rollout(W)
+    barrier()
+
+    # ---------------- timed region 1: device-resident rollout, K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                      # evict L2 between timed steps (outside the event pair)
+        ev[i][0].record()
+        env.rollout(1)                     # 2 kernel launches: k_dynamics, k_lidar_obs
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    agent_steps_total = E * N_AGENTS * K * world
+    value = agent_steps_total / (ms_max * 1e-3)
+
+    # ---------------- per-kernel time for the roofline line (CUDA events around each launch, live)
+    kr = min(K, 100)
+    ms_dyn, ms_lid = env.rollout_timed(kr)
+    lid_s = ms_lid * 1e-3 / kr
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    else:
+        peak, peak_src = 6650.0, "fallback"
+    achieved = ALGO_BYTES_PER_AGENT_STEP * E * N_AGENTS / lid_s / 1e9
+    traffic = None
+    rp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(rp):
+        try:
+            traffic = json.load(open(rp)).get("k_lidar_obs_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_lidar_obs", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "us_per_launch": lid_s * 1e6,
+                "k_dynamics_us_per_launch": ms_dyn * 1e3 / kr,
+                "note": "path is issue-bound, not HBM-bound (SURVEY.md §8d): see profiles/ for issue-slot utilisation"}
+
+    # ---------------- timed region 2: end to end through the public API with HOST buffers
+    Ke = min(K, 50)
+    rng = np.random.default_rng(rank)
+    acts = [rng.uniform(-1, 1, (E, N_AGENTS, 2)).astype(np.float32) for _ in range(4)]
+    for i in range(3):
+        env.step_host(acts[i % 4], DT)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        env.step_host(acts[i % 4], DT)     # H2D actions, 2 kernels, D2H obs/reward/done/status/terminated/truncated, sync
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = E * N_AGENTS * Ke * world / float(te.item())
+    h2d = E * N_AGENTS * 2 * 4
+    d2h = E * N_AGENTS * (127 * 4 + 4 + 1 + 1) + 2 * E
+
+    # ---------------- the one collective: all-reduce(sum) of the episode counters
+    st = env.stats_tensor().clone()
+    if world > 1:
+        counters = st.clone()
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    else:
+        counters = st
+    counters = counters.cpu().tolist()
+    stats = {"agent_steps": counters[11], "status_hist": counters[0:6], "npc_spawned": counters[6], "npc_removed": counters[7],
+             "npc_collided": counters[8], "npc_overflow": counters[9], "env_resets": counters[10]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            v, _, info = cpu_reference_run(samples=4, warmup=1, steps_per_sample=100, threads=threads)
+            cpu_baseline = dict(info, value=v, unit=UNIT)
+        except Exception as ex:  # the checker libraries did not travel: report, do not fail the bench
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world, E),
+            "clocks": clocks, "gpu_launches": 2 * K,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "stats": stats, "wall_s_timed_region": t_wall,
+            "target_1e9_frac": value / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

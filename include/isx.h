@@ -151,6 +151,10 @@ int isx_step_host(isx_handle *h, const float *actions, float dt, float *obs, flo
  * (DESIGN.md "RNG streams"); with auto_reset this is the random-action rollout BASELINE.json quotes. */
 int isx_rollout(isx_handle *h, int32_t steps, float dt, void *stream);
 
+/* isx_rollout with a CUDA-event pair around each kernel launch (on `stream`); returns the summed device
+ * milliseconds of the dynamics kernel and of the lidar+observation kernel.  Synchronous.  Measurement aid. */
+int isx_rollout_timed(isx_handle *h, int32_t steps, float dt, void *stream, float *ms_dynamics, float *ms_lidar_obs);
+
 int isx_get_buffers(isx_handle *h, isx_buffers *out);
 int isx_num_envs(isx_handle *h);
 int isx_num_agents(isx_handle *h);

@@ -1,0 +1,220 @@
+"""Batched front-end: E env instances stepping in lockstep on one B200 through libisx_b200.so.
+
+Mirrors the reference's ``IntersectionEnv`` reset()/step() contract (/root/reference/env.py:147-208) with a
+leading env dimension: ``reset() -> obs[E,N,127]``; ``step(actions[E,N,2], dt) -> obs, reward[E,N],
+terminated[E], truncated[E], info``.  Every returned tensor is a NON-OWNING view of a device buffer that the
+library overwrites on the next step (the reference returns by-value copies, bindings.cpp:60-62)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .utils import STATUS_NAMES, all_default_routes, default_ego_routes, reward_vector
+
+_NP = {"f4": np.float32, "u1": np.uint8, "i4": np.int32, "u4": np.uint32}
+_TORCH_VIEW = {"u4": "i4"}  # torch has no uint32 arithmetic; expose as int32 bits
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can wrap a raw device pointer without copying."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<" + typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+        self._owner = owner
+
+
+def _strarr(items: Sequence[str]):
+    arr = (C.c_char_p * max(len(items), 1))()
+    for i, s in enumerate(items):
+        arr[i] = s.encode()
+    return arr
+
+
+class BatchedIntersectionEnv:
+    """config keys (all optional): num_envs, num_agents, num_lanes, ego_routes, use_team_reward,
+    respawn_enabled, max_steps, traffic_flow, traffic_density, traffic_routes, reward_config, lidar_rays (96|72),
+    npc_capacity, seed, device, env_id_base, auto_reset."""
+
+    def __init__(self, config: Optional[Dict[str, Any]] = None):
+        cfg = dict(config or {})
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedIntersectionEnv needs a CUDA device: there is no CPU fallback")
+        self._lib = _lib.load_library()
+        self.num_envs = int(cfg.get("num_envs", 1))
+        self.num_lanes = int(cfg.get("num_lanes", 3))
+        self.traffic_flow = bool(cfg.get("traffic_flow", False))
+        self.num_agents = int(cfg.get("num_agents", 1))
+        routes = cfg.get("ego_routes", None)
+        if routes is None:
+            routes = default_ego_routes(self.num_agents, self.num_lanes)   # env.py:138-145
+        routes = [(str(a), str(b)) for a, b in routes]
+        if len(routes) != self.num_agents:
+            raise ValueError(f"ego_routes has {len(routes)} entries for num_agents={self.num_agents}")
+        self.ego_routes = routes
+        troutes = cfg.get("traffic_routes", None)
+        if troutes is None:
+            troutes = all_default_routes(self.num_lanes)                   # env.py:118-123
+        self.traffic_routes = [(str(a), str(b)) for a, b in troutes]
+        dev = cfg.get("device", None)
+        self.device_index = torch.cuda.current_device() if dev is None else torch.device(dev).index or 0
+        self.device = torch.device("cuda", self.device_index)
+        self.lidar_rays = int(cfg.get("lidar_rays", 96))
+        self.max_steps = int(cfg.get("max_steps", 2000))
+
+        c = _lib.Config()
+        c.abi_version = _lib.ISX_ABI_VERSION
+        c.device = self.device_index
+        c.num_envs = self.num_envs
+        c.num_agents = self.num_agents
+        c.num_lanes = self.num_lanes
+        c.lidar_rays = self.lidar_rays
+        c.npc_capacity = int(cfg.get("npc_capacity", 16))
+        c.use_team_reward = int(bool(cfg.get("use_team_reward", False)))
+        c.respawn_enabled = int(bool(cfg.get("respawn_enabled", True)))
+        c.max_steps = self.max_steps
+        c.traffic_flow = int(self.traffic_flow)
+        c.traffic_density = float(cfg.get("traffic_density", 0.5))
+        for i, v in enumerate(reward_vector(cfg.get("reward_config", None))):
+            c.reward[i] = v
+        self._keep = [_strarr([a for a, _ in routes]), _strarr([b for _, b in routes]),
+                      _strarr([a for a, _ in self.traffic_routes]), _strarr([b for _, b in self.traffic_routes])]
+        c.ego_start, c.ego_end = self._keep[0], self._keep[1]
+        c.num_traffic_routes = len(self.traffic_routes)
+        c.traffic_start, c.traffic_end = self._keep[2], self._keep[3]
+        c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
+        c.env_id_base = int(cfg.get("env_id_base", 0))
+        c.auto_reset = int(bool(cfg.get("auto_reset", False)))
+        self._h = C.c_void_p()
+        rc = self._lib.isx_create(C.byref(c), C.byref(self._h))
+        if rc == _lib.E_ROUTE_END:
+            raise IndexError(self._lib.isx_last_error().decode())       # std::out_of_range -> IndexError in the reference
+        _lib.check(self._lib, rc)
+        self.npc_capacity = c.npc_capacity if self.traffic_flow else 1
+        self._wrap_buffers()
+
+    # ------------------------------------------------------------------ buffers
+    def _wrap_buffers(self):
+        b = _lib.Buffers()
+        _lib.check(self._lib, self._lib.isx_get_buffers(self._h, C.byref(b)))
+        E, N, M = self.num_envs, self.num_agents, self.npc_capacity
+        shapes = {
+            "obs": (E, N, _lib.OBS_DIM), "reward": (E, N), "done": (E, N), "status": (E, N), "terminated": (E,),
+            "truncated": (E,), "agents_alive": (E,), "step": (E,), "lidar_hit": (E, N, _lib.MAX_RAYS),
+            "npc_count": (E,), "tick": (E,),
+        }
+        self.buf: Dict[str, torch.Tensor] = {}
+        for name, ts in _lib._BUF_FIELDS:
+            ptr = getattr(b, name)
+            if name == "events":
+                shape, t = (E, 6), "i4"
+            else:
+                t = _TORCH_VIEW.get(ts, ts)
+                if name in shapes:
+                    shape = shapes[name]
+                elif name.startswith("ego_"):
+                    shape = (E, N)
+                else:
+                    shape = (E, M)
+            with torch.cuda.device(self.device):
+                self.buf[name] = torch.as_tensor(_DevArray(ptr, shape, t, self), device=self.device)
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ API
+    def reset(self, mask: Optional[torch.Tensor] = None):
+        """reset() + add_car_with_route for every env (or those where mask != 0).  Returns (obs, {})."""
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if mask.numel() != self.num_envs:
+                raise ValueError("mask must have num_envs elements")
+            mp = C.c_void_p(mask.data_ptr())
+        _lib.check(self._lib, self._lib.isx_reset(self._h, mp, self._stream()))
+        return self.buf["obs"], {}
+
+    def step(self, actions: torch.Tensor, dt: float = 1.0 / 60.0):
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.numel() != self.num_envs * self.num_agents * 2:
+            raise ValueError(f"Expected actions shape ({self.num_envs},{self.num_agents},2), got {tuple(actions.shape)}")
+        _lib.check(self._lib, self._lib.isx_step(self._h, C.c_void_p(a.data_ptr()), C.c_float(dt), self._stream()))
+        b = self.buf
+        info = {"done": b["done"], "status": b["status"], "agents_alive": b["agents_alive"], "step": b["step"],
+                "lidar_hit": b["lidar_hit"], "npc_count": b["npc_count"], "events": b["events"]}
+        return b["obs"], b["reward"], b["terminated"].bool(), b["truncated"].bool(), info
+
+    def step_host(self, actions: np.ndarray, dt: float = 1.0 / 60.0):
+        """The same step through HOST buffers (what env.py's list<->numpy conversions amount to)."""
+        E, N = self.num_envs, self.num_agents
+        a = np.ascontiguousarray(np.asarray(actions, dtype=np.float32).reshape(E, N, 2))
+        obs = np.empty((E, N, _lib.OBS_DIM), np.float32)
+        rew = np.empty((E, N), np.float32)
+        done = np.empty((E, N), np.uint8)
+        status = np.empty((E, N), np.uint8)
+        term = np.empty(E, np.uint8)
+        trunc = np.empty(E, np.uint8)
+        _lib.check(self._lib, self._lib.isx_step_host(self._h, a.ctypes.data, C.c_float(dt), obs.ctypes.data, rew.ctypes.data,
+                                                       done.ctypes.data, status.ctypes.data, term.ctypes.data, trunc.ctypes.data,
+                                                       self._stream()))
+        return obs, rew, done, status, term.astype(bool), trunc.astype(bool)
+
+    def rollout(self, steps: int, dt: float = 1.0 / 60.0):
+        """`steps` steps with on-device Philox actions (random-action rollout of BASELINE.json)."""
+        _lib.check(self._lib, self._lib.isx_rollout(self._h, int(steps), C.c_float(dt), self._stream()))
+
+    def rollout_timed(self, steps: int, dt: float = 1.0 / 60.0):
+        """rollout() with per-kernel CUDA-event timing; returns (ms in k_dynamics, ms in k_lidar_obs)."""
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self._lib, self._lib.isx_rollout_timed(self._h, int(steps), C.c_float(dt), self._stream(), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def observe(self):
+        _lib.check(self._lib, self._lib.isx_observe(self._h, self._stream()))
+        return self.buf["obs"]
+
+    def stats(self) -> Dict[str, Any]:
+        s = _lib.Stats()
+        torch.cuda.synchronize(self.device)
+        _lib.check(self._lib, self._lib.isx_stats_read(self._h, C.byref(s)))
+        return {"agent_steps": s.agent_steps, "status_hist": {STATUS_NAMES[i]: s.status_hist[i] for i in range(6)},
+                "npc_spawned": s.npc_spawned, "npc_removed": s.npc_removed, "npc_collided": s.npc_collided,
+                "npc_overflow": s.npc_overflow, "env_resets": s.env_resets, "reward_sum": s.reward_sum}
+
+    def stats_tensor(self) -> torch.Tensor:
+        """int64[16] device view of the reduced counters (slot 15 = reward_sum bits) for an NCCL all-reduce."""
+        p, n = C.c_void_p(), C.c_int32()
+        _lib.check(self._lib, self._lib.isx_stats_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return torch.as_tensor(_DevArray(p.value, (n.value,), "i8", self), device=self.device)
+
+    def reset_stats(self):
+        _lib.check(self._lib, self._lib.isx_stats_reset(self._h))
+
+    def get_env_state(self, env: int):
+        N, M = self.num_agents, self.npc_capacity
+        egos = (_lib.CarState * N)()
+        npcs = (_lib.CarState * M)()
+        n, sc, tk = C.c_int32(), C.c_int32(), C.c_uint32()
+        _lib.check(self._lib, self._lib.isx_get_env_state(self._h, env, egos, npcs, M, C.byref(n), C.byref(sc), C.byref(tk)))
+        return egos, npcs, n.value, sc.value, tk.value
+
+    def set_env_state(self, env: int, egos, npcs, n_npcs: int, step_count: int, tick: int):
+        _lib.check(self._lib, self._lib.isx_set_env_state(self._h, env, egos, npcs, int(n_npcs), int(step_count), int(tick)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.buf = {}
+            self._lib.isx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

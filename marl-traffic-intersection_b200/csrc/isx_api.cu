@@ -1,0 +1,503 @@
+// isx_api.cu — C ABI of libisx_b200.so (include/isx.h): handle lifetime, table upload, launches,
+// host<->device staging.  All simulation work happens in isx_kernels.cu on the GPU; nothing here steps an env.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "isx_device.cuh"
+#include "isx_tables.h"
+
+namespace isx {
+size_t lidar_smem_bytes(const Dev& d);
+cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float spawn_prob, cudaStream_t st);
+cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st);
+cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st);
+cudaError_t launch_reduce_stats(const Dev& d, cudaStream_t st);
+cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st);
+cudaError_t launch_math_probe(int n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr, cudaStream_t st);
+cudaError_t lidar_set_smem_attr(const Dev& d);
+cudaError_t lidar_occupancy(const Dev& d, int* ctas_per_sm);
+}  // namespace isx
+
+using namespace isx;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(ISX_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct isx_handle {
+    Dev d{};
+    isx_config cfg{};
+    int device = 0;
+    int lidar_grid = 0;
+    std::vector<void*> allocs;
+    // pinned staging for isx_step_host
+    float* h_actions = nullptr; float* d_actions = nullptr;
+    float* h_obs = nullptr; float* h_reward = nullptr;
+    uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;
+    float last_dt = -1.0f, last_prob = 0.0f;
+    std::vector<RouteHost> routes;
+};
+
+template <class T>
+static int dev_alloc(isx_handle* h, T** p, size_t n, bool zero = true) {
+    void* q = nullptr;
+    const size_t bytes = sizeof(T) * (n ? n : 1);
+    CK(cudaMalloc(&q, bytes));
+    if (zero) CK(cudaMemset(q, 0, bytes));
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+template <class T>
+static cudaError_t pull(std::vector<T>& v, const T* dev, size_t off, size_t n) {
+    v.resize(n ? n : 1);
+    return cudaMemcpy(v.data(), dev + off, sizeof(T) * n, cudaMemcpyDeviceToHost);
+}
+template <class T>
+static cudaError_t push(const std::vector<T>& v, T* dev, size_t off, size_t n) {
+    return cudaMemcpy(dev + off, v.data(), sizeof(T) * n, cudaMemcpyHostToDevice);
+}
+
+extern "C" {
+
+const char* isx_last_error(void) { return g_err.c_str(); }
+int isx_abi_version(void) { return ISX_ABI_VERSION; }
+
+int isx_route(int32_t lanes, const char* start, const char* end, float* path_xy, int32_t* intent, float* sx, float* sy, float* sh) {
+    if (!start || !end) return fail(ISX_E_ARG, "null lane id");
+    RouteHost r;
+    const int rc = build_route(lanes, start, end, &r);
+    if (rc == -1) return fail(ISX_E_ROUTE_START, "unknown start lane id '%s'", start);
+    if (rc == -2) return fail(ISX_E_ROUTE_END, "unknown end lane id '%s'", end);
+    if (path_xy) for (int i = 0; i < PATH_LEN; ++i) { path_xy[2 * i] = r.path[i].x; path_xy[2 * i + 1] = r.path[i].y; }
+    if (intent) *intent = r.intent;
+    if (sx) *sx = r.spawn_x;
+    if (sy) *sy = r.spawn_y;
+    if (sh) *sh = r.spawn_h;
+    return PATH_LEN;
+}
+
+int isx_create(const isx_config* cfg, isx_handle** out) {
+    if (!cfg || !out) return fail(ISX_E_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != ISX_ABI_VERSION) return fail(ISX_E_ARG, "abi_version %d != %d", cfg->abi_version, ISX_ABI_VERSION);
+    if (cfg->num_envs < 1) return fail(ISX_E_ARG, "num_envs must be >= 1");
+    if (cfg->num_agents < 1 || cfg->num_agents > ISX_MAX_AGENTS) return fail(ISX_E_ARG, "num_agents must be in [1,%d]", ISX_MAX_AGENTS);
+    if (cfg->num_lanes < 1 || cfg->num_lanes > 4) return fail(ISX_E_ARG, "num_lanes must be in [1,4]");
+    if (cfg->lidar_rays < 1 || cfg->lidar_rays > ISX_MAX_RAYS) return fail(ISX_E_ARG, "lidar_rays must be in [1,%d]", ISX_MAX_RAYS);
+    if (cfg->npc_capacity < 0 || cfg->npc_capacity > ISX_MAX_NPC) return fail(ISX_E_ARG, "npc_capacity must be in [0,%d]", ISX_MAX_NPC);
+    if (cfg->num_traffic_routes < 0 || cfg->num_traffic_routes > ISX_MAX_ROUTES) return fail(ISX_E_ARG, "num_traffic_routes must be in [0,%d]", ISX_MAX_ROUTES);
+    if ((long long)cfg->num_envs * cfg->num_agents > (1ll << 27)) return fail(ISX_E_ARG, "num_envs * num_agents too large");
+    if (!cfg->ego_start || !cfg->ego_end) return fail(ISX_E_ARG, "ego routes missing");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ISX_E_CUDA, "no CUDA device: this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(ISX_E_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+
+    isx_handle* h = new isx_handle();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    Dev& d = h->d;
+    d.E = cfg->num_envs; d.N = cfg->num_agents; d.M = cfg->traffic_flow ? (cfg->npc_capacity > 0 ? cfg->npc_capacity : 16) : 1;
+    d.R = cfg->lidar_rays; d.lanes = cfg->num_lanes;
+    d.use_team = cfg->use_team_reward != 0; d.respawn = cfg->respawn_enabled != 0; d.max_steps = cfg->max_steps;
+    d.traffic = cfg->traffic_flow != 0; d.T = cfg->num_traffic_routes; d.auto_reset = cfg->auto_reset != 0;
+    d.rc = RewardCfg{cfg->reward[0], cfg->reward[1], cfg->reward[2], cfg->reward[3], cfg->reward[4], cfg->reward[5], cfg->reward[6], cfg->reward[7]};
+    d.max_progress = hypotf_((float)WIDTH, (float)HEIGHT);
+    d.seed = cfg->seed; d.env_base = cfg->env_id_base;
+    if (d.traffic && d.T > 0 && (!cfg->traffic_start || !cfg->traffic_end)) { delete h; return fail(ISX_E_ARG, "traffic routes missing"); }
+
+    // ---- route LUT: ego slots then traffic routes
+    const int nroutes = d.N + d.T;
+    h->routes.resize((size_t)nroutes);
+    for (int i = 0; i < nroutes; ++i) {
+        const char* s = i < d.N ? cfg->ego_start[i] : cfg->traffic_start[i - d.N];
+        const char* e = i < d.N ? cfg->ego_end[i] : cfg->traffic_end[i - d.N];
+        if (!s || !e) { delete h; return fail(ISX_E_ARG, "null lane id in route %d", i); }
+        const int rc = build_route(d.lanes, s, e, &h->routes[(size_t)i]);
+        if (rc == -1) { delete h; return fail(ISX_E_ROUTE_START, "unknown start lane id '%s' (route %d)", s, i); }
+        if (rc == -2) { delete h; return fail(ISX_E_ROUTE_END, "unknown end lane id '%s' (route %d)", e, i); }
+    }
+    std::vector<F2> paths((size_t)nroutes * PATH_LEN);
+    std::vector<RouteMeta> meta((size_t)nroutes);
+    for (int i = 0; i < nroutes; ++i) {
+        const RouteHost& r = h->routes[(size_t)i];
+        std::memcpy(&paths[(size_t)i * PATH_LEN], r.path, sizeof(F2) * PATH_LEN);
+        meta[(size_t)i] = RouteMeta{r.spawn_x, r.spawn_y, r.spawn_h, r.intent, r.path[PATH_LEN - 1], r.path[PATH_LEN - 2]};
+    }
+    RoadTables rt;
+    if (!build_road_tables(d.lanes, &rt)) { delete h; return fail(ISX_E_STATE, "road map is not mirror-symmetric"); }
+    std::vector<float> rel((size_t)ISX_MAX_RAYS, 0.0f);
+    lidar_rel_angles(d.R, rel.data());
+
+#define ALLOC(ptr, n)                                     \
+    do {                                                  \
+        int rc_ = dev_alloc(h, &(ptr), (size_t)(n));      \
+        if (rc_) { isx_destroy(h); return rc_; }          \
+    } while (0)
+#define UPLOAD(dst, src, bytes)                                                                  \
+    do {                                                                                         \
+        cudaError_t e_ = cudaMemcpy((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice);       \
+        if (e_ != cudaSuccess) { isx_destroy(h); return fail(ISX_E_CUDA, "upload failed: %s", cudaGetErrorString(e_)); } \
+    } while (0)
+
+    F2* d_paths; RouteMeta* d_meta; uint32_t* d_bits; uint8_t* d_skip; float* d_rel;
+    ALLOC(d_paths, paths.size()); UPLOAD(d_paths, paths.data(), sizeof(F2) * paths.size());
+    ALLOC(d_meta, meta.size()); UPLOAD(d_meta, meta.data(), sizeof(RouteMeta) * meta.size());
+    ALLOC(d_bits, rt.bits.size()); UPLOAD(d_bits, rt.bits.data(), sizeof(uint32_t) * rt.bits.size());
+    ALLOC(d_skip, rt.skip.size()); UPLOAD(d_skip, rt.skip.data(), rt.skip.size());
+    ALLOC(d_rel, rel.size()); UPLOAD(d_rel, rel.data(), sizeof(float) * rel.size());
+    d.route_path = d_paths; d.route_meta = d_meta; d.road_bits = d_bits; d.road_skip = d_skip; d.rel_angle = d_rel;
+
+    const size_t EN = (size_t)d.E * d.N, EM = (size_t)d.E * d.M, E = (size_t)d.E;
+    ALLOC(d.ex, EN); ALLOC(d.ey, EN); ALLOC(d.ev, EN); ALLOC(d.eh, EN); ALLOC(d.esteer, EN); ALLOC(d.eacc, EN);
+    ALLOC(d.epd, EN); ALLOC(d.epa0, EN); ALLOC(d.epa1, EN); ALLOC(d.epidx, EN); ALLOC(d.ealive, EN);
+    ALLOC(d.nx, EM); ALLOC(d.ny, EM); ALLOC(d.nv, EM); ALLOC(d.nh, EM); ALLOC(d.nsteer, EM);
+    ALLOC(d.npidx, EM); ALLOC(d.nroute, EM); ALLOC(d.nuid, EM);
+    ALLOC(d.ncount, E); ALLOC(d.next_uid, E); ALLOC(d.step_count, E); ALLOC(d.tick, E);
+    ALLOC(d.obs, EN * ISX_OBS_DIM); ALLOC(d.reward, EN); ALLOC(d.done, EN); ALLOC(d.status, EN);
+    ALLOC(d.terminated, E); ALLOC(d.truncated, E); ALLOC(d.agents_alive, E);
+    ALLOC(d.lidar_hit, EN * ISX_MAX_RAYS); ALLOC(d.events, E);
+    ALLOC(d.env_stats, E * STAT_SLOTS); ALLOC(d.stats, 16);
+    ALLOC(h->d_actions, EN * 2);
+#undef ALLOC
+#undef UPLOAD
+
+    // ---- contraction canary: the build must not fuse a*b+c (isx_math.cuh); fail loudly if it does
+    {
+        float* d_out = reinterpret_cast<float*>(d.stats);
+        const float a = 1.0f + 0x1p-12f, b = 1.0f + 0x1p-12f, c = -1.0f;   // a*b rounds; fma keeps the 2^-24 term
+        cudaError_t e = launch_canary(a, b, c, d_out, 0);
+        float res[2] = {0, 0};
+        if (e == cudaSuccess) e = cudaMemcpy(res, d_out, sizeof res, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { isx_destroy(h); return fail(ISX_E_CUDA, "self-test launch failed: %s", cudaGetErrorString(e)); }
+        const volatile float prod = a * b;
+        const float expect = prod + c;
+        if (std::memcmp(&res[0], &expect, 4) != 0) { isx_destroy(h); return fail(ISX_E_STATE, "library was built with FMA contraction on; rebuild with -fmad=false"); }
+        cudaMemset(d.stats, 0, 16 * sizeof(unsigned long long));
+    }
+    {
+        cudaError_t e = lidar_set_smem_attr(d);
+        int per_sm = 0, sms = 0;
+        if (e == cudaSuccess) e = lidar_occupancy(d, &per_sm);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        if (e != cudaSuccess || per_sm < 1) { isx_destroy(h); return fail(ISX_E_CUDA, "lidar kernel cannot be scheduled: %s", cudaGetErrorString(e)); }
+        h->lidar_grid = per_sm * sms;
+    }
+    // pinned staging
+    if (cudaMallocHost((void**)&h->h_actions, sizeof(float) * EN * 2) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_obs, sizeof(float) * EN * ISX_OBS_DIM) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_reward, sizeof(float) * EN) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_done, EN) != cudaSuccess || cudaMallocHost((void**)&h->h_status, EN) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_term, E) != cudaSuccess || cudaMallocHost((void**)&h->h_trunc, E) != cudaSuccess) {
+        isx_destroy(h);
+        return fail(ISX_E_CUDA, "pinned host allocation failed");
+    }
+    *out = h;
+    const int rc = isx_reset(h, nullptr, nullptr);
+    if (rc) { isx_destroy(h); *out = nullptr; return rc; }
+    CK(cudaDeviceSynchronize());
+    return ISX_OK;
+}
+
+int isx_destroy(isx_handle* h) {
+    if (!h) return ISX_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_actions) cudaFreeHost(h->h_actions);
+    if (h->h_obs) cudaFreeHost(h->h_obs);
+    if (h->h_reward) cudaFreeHost(h->h_reward);
+    if (h->h_done) cudaFreeHost(h->h_done);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_term) cudaFreeHost(h->h_term);
+    if (h->h_trunc) cudaFreeHost(h->h_trunc);
+    delete h;
+    return ISX_OK;
+}
+
+int isx_num_envs(isx_handle* h) { return h ? h->d.E : fail(ISX_E_ARG, "null handle"); }
+int isx_num_agents(isx_handle* h) { return h ? h->d.N : fail(ISX_E_ARG, "null handle"); }
+
+int isx_reset(isx_handle* h, const uint8_t* env_mask_dev, void* stream) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    CK(launch_reset(h->d, env_mask_dev, st));
+    CK(launch_lidar_obs(h->d, /*LIDAR_FROM_HITS*/ 1, h->lidar_grid, st));
+    return ISX_OK;
+}
+
+int isx_observe(isx_handle* h, void* stream) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(launch_lidar_obs(h->d, 1, h->lidar_grid, static_cast<cudaStream_t>(stream)));
+    return ISX_OK;
+}
+
+// spawn_prob = 1 - exp(-density * dt) (TrafficFlow.cpp:321-322), evaluated on the host with the host libm's
+// expf — the same entry point the reference calls — once per distinct dt.
+static float spawn_prob_for(isx_handle* h, float dt) {
+    if (dt != h->last_dt) {
+        float dens = h->cfg.traffic_density;
+        if (dens < 0.0f) dens = 0.0f;                       // configure_traffic clamps (IntersectionEnv.cpp:59)
+        volatile float arg = -dens * dt;
+        h->last_prob = 1.0f - expf(arg);
+        h->last_dt = dt;
+    }
+    return h->last_prob;
+}
+
+int isx_step(isx_handle* h, const float* actions_dev, float dt, void* stream) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (!actions_dev) return fail(ISX_E_ARG, "actions_dev is null (use isx_rollout for on-device actions)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    CK(launch_dynamics(h->d, actions_dev, dt, spawn_prob_for(h, dt), st));
+    CK(launch_lidar_obs(h->d, 0, h->lidar_grid, st));
+    return ISX_OK;
+}
+
+int isx_rollout(isx_handle* h, int32_t steps, float dt, void* stream) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (steps < 0) return fail(ISX_E_ARG, "steps < 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const float prob = spawn_prob_for(h, dt);
+    for (int s = 0; s < steps; ++s) {
+        CK(launch_dynamics(h->d, nullptr, dt, prob, st));
+        CK(launch_lidar_obs(h->d, 0, h->lidar_grid, st));
+    }
+    return ISX_OK;
+}
+
+// Same loop as isx_rollout, with a CUDA-event pair around every kernel on the launching stream; returns the
+// summed device time of each kernel (ms).  Synchronises.  Used by bench.py for the roofline line.
+int isx_rollout_timed(isx_handle* h, int32_t steps, float dt, void* stream, float* ms_dynamics, float* ms_lidar_obs) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (steps < 1 || steps > 4096) return fail(ISX_E_ARG, "steps must be in [1,4096]");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const float prob = spawn_prob_for(h, dt);
+    std::vector<cudaEvent_t> ev((size_t)steps * 3);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (int s = 0; s < steps; ++s) {
+        CK(cudaEventRecord(ev[(size_t)s * 3 + 0], st));
+        CK(launch_dynamics(h->d, nullptr, dt, prob, st));
+        CK(cudaEventRecord(ev[(size_t)s * 3 + 1], st));
+        CK(launch_lidar_obs(h->d, 0, h->lidar_grid, st));
+        CK(cudaEventRecord(ev[(size_t)s * 3 + 2], st));
+    }
+    CK(cudaStreamSynchronize(st));
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < steps; ++s) {
+        float t0 = 0, t1 = 0;
+        CK(cudaEventElapsedTime(&t0, ev[(size_t)s * 3 + 0], ev[(size_t)s * 3 + 1]));
+        CK(cudaEventElapsedTime(&t1, ev[(size_t)s * 3 + 1], ev[(size_t)s * 3 + 2]));
+        a += t0; b += t1;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (ms_dynamics) *ms_dynamics = (float)a;
+    if (ms_lidar_obs) *ms_lidar_obs = (float)b;
+    return ISX_OK;
+}
+
+int isx_step_host(isx_handle* h, const float* actions, float dt, float* obs, float* reward, uint8_t* done, uint8_t* status,
+                  uint8_t* terminated, uint8_t* truncated, void* stream) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (!actions) return fail(ISX_E_ARG, "actions is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const Dev& d = h->d;
+    const size_t EN = (size_t)d.E * d.N, E = (size_t)d.E;
+    std::memcpy(h->h_actions, actions, sizeof(float) * EN * 2);
+    CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * EN * 2, cudaMemcpyHostToDevice, st));
+    CK(launch_dynamics(d, h->d_actions, dt, spawn_prob_for(h, dt), st));
+    CK(launch_lidar_obs(d, 0, h->lidar_grid, st));
+    if (obs) CK(cudaMemcpyAsync(h->h_obs, d.obs, sizeof(float) * EN * ISX_OBS_DIM, cudaMemcpyDeviceToHost, st));
+    if (reward) CK(cudaMemcpyAsync(h->h_reward, d.reward, sizeof(float) * EN, cudaMemcpyDeviceToHost, st));
+    if (done) CK(cudaMemcpyAsync(h->h_done, d.done, EN, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(h->h_status, d.status, EN, cudaMemcpyDeviceToHost, st));
+    if (terminated) CK(cudaMemcpyAsync(h->h_term, d.terminated, E, cudaMemcpyDeviceToHost, st));
+    if (truncated) CK(cudaMemcpyAsync(h->h_trunc, d.truncated, E, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (obs) std::memcpy(obs, h->h_obs, sizeof(float) * EN * ISX_OBS_DIM);
+    if (reward) std::memcpy(reward, h->h_reward, sizeof(float) * EN);
+    if (done) std::memcpy(done, h->h_done, EN);
+    if (status) std::memcpy(status, h->h_status, EN);
+    if (terminated) std::memcpy(terminated, h->h_term, E);
+    if (truncated) std::memcpy(truncated, h->h_trunc, E);
+    return ISX_OK;
+}
+
+int isx_get_buffers(isx_handle* h, isx_buffers* b) {
+    if (!h || !b) return fail(ISX_E_ARG, "null argument");
+    const Dev& d = h->d;
+    b->obs = d.obs; b->reward = d.reward; b->done = d.done; b->status = d.status;
+    b->terminated = d.terminated; b->truncated = d.truncated; b->agents_alive = d.agents_alive; b->step = d.step_count;
+    b->lidar_hit = d.lidar_hit;
+    b->ego_x = d.ex; b->ego_y = d.ey; b->ego_v = d.ev; b->ego_heading = d.eh; b->ego_steer = d.esteer; b->ego_acc = d.eacc;
+    b->ego_prev_dist = d.epd; b->ego_prev_a0 = d.epa0; b->ego_prev_a1 = d.epa1; b->ego_path_index = d.epidx; b->ego_alive = d.ealive;
+    b->npc_x = d.nx; b->npc_y = d.ny; b->npc_v = d.nv; b->npc_heading = d.nh; b->npc_steer = d.nsteer;
+    b->npc_path_index = d.npidx; b->npc_route = d.nroute; b->npc_uid = d.nuid; b->npc_count = d.ncount;
+    b->events = d.events; b->tick = d.tick;
+    return ISX_OK;
+}
+
+int isx_get_env_state(isx_handle* h, int32_t env, isx_car_state* egos, isx_car_state* npcs, int32_t cap, int32_t* n_npcs,
+                      int32_t* step_count, uint32_t* tick) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    const Dev& d = h->d;
+    if (env < 0 || env >= d.E) return fail(ISX_E_ARG, "env %d out of range", env);
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const size_t N = (size_t)d.N, M = (size_t)d.M, eo = (size_t)env * N, no = (size_t)env * M;
+    std::vector<float> x, y, v, hd, st, ac, pdv, a0, a1;
+    std::vector<int> pi, rt;
+    std::vector<uint8_t> al;
+    std::vector<uint32_t> uid;
+    if (egos) {
+        CK(pull(x, d.ex, eo, N)); CK(pull(y, d.ey, eo, N)); CK(pull(v, d.ev, eo, N)); CK(pull(hd, d.eh, eo, N));
+        CK(pull(st, d.esteer, eo, N)); CK(pull(ac, d.eacc, eo, N)); CK(pull(pdv, d.epd, eo, N)); CK(pull(a0, d.epa0, eo, N));
+        CK(pull(a1, d.epa1, eo, N)); CK(pull(pi, d.epidx, eo, N)); CK(pull(al, d.ealive, eo, N));
+        for (size_t i = 0; i < N; ++i)
+            egos[i] = isx_car_state{x[i], y[i], v[i], hd[i], ac[i], st[i], pdv[i], a0[i], a1[i], pi[i], (int32_t)i, al[i] ? 1 : 0, 0u, h->routes[i].intent};
+    }
+    int cnt = 0;
+    if (d.traffic) CK(cudaMemcpy(&cnt, d.ncount + env, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n_npcs) *n_npcs = cnt;
+    if (npcs && cnt > 0) {
+        CK(pull(x, d.nx, no, M)); CK(pull(y, d.ny, no, M)); CK(pull(v, d.nv, no, M)); CK(pull(hd, d.nh, no, M));
+        CK(pull(st, d.nsteer, no, M)); CK(pull(pi, d.npidx, no, M)); CK(pull(rt, d.nroute, no, M)); CK(pull(uid, d.nuid, no, M));
+        for (int i = 0; i < cnt && i < cap; ++i) {
+            const size_t k = (size_t)i;
+            npcs[i] = isx_car_state{x[k], y[k], v[k], hd[k], 0.0f, st[k], 0.0f, 0.0f, 0.0f, pi[k], rt[k], 1, uid[k], h->routes[N + (size_t)rt[k]].intent};
+        }
+    }
+    if (step_count) CK(cudaMemcpy(step_count, d.step_count + env, sizeof(int), cudaMemcpyDeviceToHost));
+    if (tick) CK(cudaMemcpy(tick, d.tick + env, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return ISX_OK;
+}
+
+int isx_set_env_state(isx_handle* h, int32_t env, const isx_car_state* egos, const isx_car_state* npcs, int32_t n_npcs,
+                      int32_t step_count, uint32_t tick) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    const Dev& d = h->d;
+    if (env < 0 || env >= d.E) return fail(ISX_E_ARG, "env %d out of range", env);
+    if (n_npcs < 0 || n_npcs > d.M || (n_npcs > 0 && !d.traffic)) return fail(ISX_E_ARG, "n_npcs %d exceeds capacity %d", n_npcs, d.traffic ? d.M : 0);
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const size_t N = (size_t)d.N, eo = (size_t)env * N, no = (size_t)env * d.M;
+    if (egos) {
+        std::vector<float> x(N), y(N), v(N), hd(N), st(N), ac(N), pdv(N), a0(N), a1(N);
+        std::vector<int> pi(N);
+        std::vector<uint8_t> al(N);
+        for (size_t i = 0; i < N; ++i) {
+            x[i] = egos[i].x; y[i] = egos[i].y; v[i] = egos[i].v; hd[i] = egos[i].heading; st[i] = egos[i].steer; ac[i] = egos[i].acc;
+            pdv[i] = egos[i].prev_dist; a0[i] = egos[i].prev_a0; a1[i] = egos[i].prev_a1; pi[i] = egos[i].path_index; al[i] = egos[i].alive ? 1 : 0;
+            if (pi[i] < 0 || pi[i] >= PATH_LEN) return fail(ISX_E_ARG, "path_index out of range");
+        }
+        CK(push(x, d.ex, eo, N)); CK(push(y, d.ey, eo, N)); CK(push(v, d.ev, eo, N)); CK(push(hd, d.eh, eo, N));
+        CK(push(st, d.esteer, eo, N)); CK(push(ac, d.eacc, eo, N)); CK(push(pdv, d.epd, eo, N)); CK(push(a0, d.epa0, eo, N));
+        CK(push(a1, d.epa1, eo, N)); CK(push(pi, d.epidx, eo, N)); CK(push(al, d.ealive, eo, N));
+    }
+    if (d.traffic) {
+        const size_t K = (size_t)n_npcs;
+        if (K > 0) {
+            if (!npcs) return fail(ISX_E_ARG, "npcs is null");
+            std::vector<float> x(K), y(K), v(K), hd(K), st(K);
+            std::vector<int> pi(K), rt(K);
+            std::vector<uint32_t> uid(K);
+            uint32_t max_uid = 0;
+            for (size_t i = 0; i < K; ++i) {
+                x[i] = npcs[i].x; y[i] = npcs[i].y; v[i] = npcs[i].v; hd[i] = npcs[i].heading; st[i] = npcs[i].steer;
+                pi[i] = npcs[i].path_index; rt[i] = npcs[i].route; uid[i] = npcs[i].uid;
+                if (rt[i] < 0 || rt[i] >= d.T) return fail(ISX_E_ARG, "npc route %d out of range", rt[i]);
+                if (pi[i] < 0 || pi[i] >= PATH_LEN) return fail(ISX_E_ARG, "path_index out of range");
+                if (uid[i] > max_uid) max_uid = uid[i];
+            }
+            CK(push(x, d.nx, no, K)); CK(push(y, d.ny, no, K)); CK(push(v, d.nv, no, K)); CK(push(hd, d.nh, no, K));
+            CK(push(st, d.nsteer, no, K)); CK(push(pi, d.npidx, no, K)); CK(push(rt, d.nroute, no, K)); CK(push(uid, d.nuid, no, K));
+            uint32_t nu = 0;
+            CK(cudaMemcpy(&nu, d.next_uid + env, 4, cudaMemcpyDeviceToHost));
+            if (max_uid >= nu) { nu = max_uid + 1; CK(cudaMemcpy(d.next_uid + env, &nu, 4, cudaMemcpyHostToDevice)); }
+        }
+        CK(cudaMemcpy(d.ncount + env, &n_npcs, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpy(d.step_count + env, &step_count, sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.tick + env, &tick, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return ISX_OK;
+}
+
+int isx_stats_read(isx_handle* h, isx_stats* out) {
+    if (!h || !out) return fail(ISX_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(launch_reduce_stats(h->d, 0));
+    unsigned long long raw[16];
+    CK(cudaMemcpy(raw, h->d.stats, sizeof raw, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) out->status_hist[i] = (int64_t)raw[ST_HIST0 + i];
+    out->npc_spawned = (int64_t)raw[ST_SPAWNED]; out->npc_removed = (int64_t)raw[ST_REMOVED];
+    out->npc_collided = (int64_t)raw[ST_COLLIDED]; out->npc_overflow = (int64_t)raw[ST_OVERFLOW];
+    out->env_resets = (int64_t)raw[ST_RESETS]; out->agent_steps = (int64_t)raw[ST_STEPS];
+    std::memcpy(&out->reward_sum, &raw[15], 8);
+    return ISX_OK;
+}
+int isx_stats_reset(isx_handle* h) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(h->d.env_stats, 0, sizeof(uint32_t) * (size_t)h->d.E * STAT_SLOTS));
+    CK(cudaMemset(h->d.stats, 0, sizeof(unsigned long long) * 16));
+    return ISX_OK;
+}
+int isx_stats_device_ptr(isx_handle* h, void** ptr, int32_t* n) {
+    if (!h || !ptr) return fail(ISX_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(launch_reduce_stats(h->d, 0));
+    CK(cudaDeviceSynchronize());
+    *ptr = h->d.stats;
+    if (n) *n = 16;
+    return ISX_OK;
+}
+
+int isx_math_probe(int32_t device, int32_t n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr) {
+    if (n <= 0 || !a || !b) return fail(ISX_E_ARG, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ISX_E_CUDA, "no CUDA device");
+    CK(cudaSetDevice(device));
+    float* buf = nullptr;
+    const size_t N = (size_t)n;
+    CK(cudaMalloc((void**)&buf, sizeof(float) * N * 8));
+    float *da = buf, *db = buf + N, *d0 = buf + 2 * N;
+    cudaError_t e = cudaMemcpy(da, a, sizeof(float) * N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, sizeof(float) * N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_math_probe(n, da, db, d0, d0 + N, d0 + 2 * N, d0 + 3 * N, d0 + 4 * N, d0 + 5 * N, 0);
+    float* outs[6] = {sn, cs, tn, at, hy, wr};
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+        if (outs[i]) e = cudaMemcpy(outs[i], d0 + (size_t)i * N, sizeof(float) * N, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(ISX_E_CUDA, "math probe failed: %s", cudaGetErrorString(e));
+    return ISX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// isx_device.cuh — device-side view of a handle: configuration + struct-of-arrays buffers in HBM.
+// Passed to every kernel by value (a few hundred bytes of kernel parameter space).
+#pragma once
+#include "../../include/isx.h"
+#include "isx_rng.cuh"
+#include "isx_sim.cuh"
+
+namespace isx {
+
+struct RouteMeta {
+    float spawn_x, spawn_y, spawn_h;
+    int intent;
+    F2 goal;        // path[159]
+    F2 goal_prev;   // path[158]
+};
+
+constexpr int STAT_SLOTS = 16;   // per-env u32 counters; slot 14/15 hold reward_sum (double)
+enum { ST_HIST0 = 0, ST_SPAWNED = 6, ST_REMOVED = 7, ST_COLLIDED = 8, ST_OVERFLOW = 9, ST_RESETS = 10, ST_STEPS = 11, ST_RSUM = 14 };
+
+struct Dev {
+    // ---- configuration
+    int E, N, M, R, lanes;
+    int use_team, respawn, max_steps, traffic, T, auto_reset;
+    RewardCfg rc;
+    float max_progress;          // hypotf(750, 750)
+    uint64_t seed;
+    long long env_base;
+    // ---- constant tables
+    const F2* route_path;        // [(N + T)][160]   ego slot i -> i, traffic route r -> N + r
+    const RouteMeta* route_meta; // [(N + T)]
+    const uint32_t* road_bits;   // [ROAD_ROWS][ROAD_WORDS]
+    const uint8_t* road_skip;    // [SKIP_DIM][SKIP_DIM]
+    const float* rel_angle;      // [R]
+    // ---- ego state [E][N]
+    float *ex, *ey, *ev, *eh, *esteer, *eacc, *epd, *epa0, *epa1;
+    int* epidx;
+    uint8_t* ealive;
+    // ---- NPC state [E][M], per-env [E]
+    float *nx, *ny, *nv, *nh, *nsteer;
+    int* npidx;
+    int* nroute;
+    uint32_t* nuid;
+    int* ncount;
+    uint32_t* next_uid;
+    int* step_count;
+    uint32_t* tick;
+    // ---- outputs
+    float* obs;                  // [E][N][127]
+    float* reward;               // [E][N]
+    uint8_t *done, *status;      // [E][N]
+    uint8_t *terminated, *truncated;   // [E]
+    int* agents_alive;           // [E]
+    uint8_t* lidar_hit;          // [E][N][96]
+    isx_traffic_events* events;  // [E]
+    uint32_t* env_stats;         // [E][STAT_SLOTS]
+    unsigned long long* stats;   // [16] reduced counters (slot 15 = reward_sum as double bits)
+};
+
+}  // namespace isx
