@@ -87,58 +87,77 @@ def cpu_reference_run(samples: int, warmup: int, steps_per_sample: int, threads:
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions (NVML, every ~5 ms, in a thread)."""
 
     def __init__(self, gpu_index: int):
-        self.proc = None
         self.gpu = gpu_index
-        self.lines = []
+        self.sm, self.reasons, self.power = [], set(), []
+        self.max_sm = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # torch's device index follows CUDA_VISIBLE_DEVICES; map through the UUID-less common case
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as ex:
+            self._err = repr(ex)
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                r = int(get_reasons(self._h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception as ex:
+                self._err = repr(ex)
+                break
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+               "reasons": sorted(self.reasons), "samples": len(self.sm),
+               "power_w_max": max(self.power) if self.power else None}
+        if self._err:
+            out["sampler_error"] = self._err
+        return out
 
 
 # ----------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,7 +229,6 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -219,7 +237,7 @@ def main():
     value = agent_steps_total / (ms_max * 1e-3)
 
     # ---------------- per-kernel time for the roofline line (CUDA events around each launch, live)
-    kr = min(K, 100)
+    kr = min(K, 200)
     ms_dyn, ms_lid = env.rollout_timed(kr)
     lid_s = ms_lid * 1e-3 / kr
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -241,7 +259,7 @@ def main():
                 "note": "path is issue-bound, not HBM-bound (SURVEY.md §8d): see profiles/ for issue-slot utilisation"}
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers
-    Ke = min(K, 50)
+    Ke = min(K, 100)
     rng = np.random.default_rng(rank)
     acts = [rng.uniform(-1, 1, (E, N_AGENTS, 2)).astype(np.float32) for _ in range(4)]
     for i in range(3):
@@ -257,6 +275,8 @@ def main():
     e2e_value = E * N_AGENTS * Ke * world / float(te.item())
     h2d = E * N_AGENTS * 2 * 4
     d2h = E * N_AGENTS * (127 * 4 + 4 + 1 + 1) + 2 * E
+
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- the one collective: all-reduce(sum) of the episode counters
     st = env.stats_tensor().clone()

@@ -168,6 +168,7 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     ALLOC(d_skip, rt.skip.size()); UPLOAD(d_skip, rt.skip.data(), rt.skip.size());
     ALLOC(d_rel, rel.size()); UPLOAD(d_rel, rel.data(), sizeof(float) * rel.size());
     d.route_path = d_paths; d.route_meta = d_meta; d.road_bits = d_bits; d.road_skip = d_skip; d.rel_angle = d_rel;
+    d.box_lo = rt.box_lo; d.box_hi = rt.box_hi;
 
     const size_t EN = (size_t)d.E * d.N, EM = (size_t)d.E * d.M, E = (size_t)d.E;
     ALLOC(d.ex, EN); ALLOC(d.ey, EN); ALLOC(d.ev, EN); ALLOC(d.eh, EN); ALLOC(d.esteer, EN); ALLOC(d.eacc, EN);

@@ -79,16 +79,16 @@ void isxh_lidar(int lanes, int rays, const float* self_pose, const float* others
     for (int i = 0; i < rays; ++i) {
         float s, c;
         sincosf_(h + rel[i], &s, &c);
-        const float dx = c, dy = -s;
+        const Ray ray = make_ray(cx, cy, c, -s);
         bool hit;
-        const int ke = ray_road_event(t->bits.data(), t->skip.data(), cx, cy, dx, dy, &hit);
+        const int ke = ray_road_event(t->bits.data(), t->skip.data(), t->box_lo, t->box_hi, ray, &hit);
         int best = hit ? ke : 0;
         const int kmax = hit ? ke - 1 : ke - 1;     // cars only count strictly before the road event
         if (kmax >= 1) {
             for (const PixRect& r : rects) {
                 const int lim = best ? best - 1 : kmax;
                 if (lim < 1) break;
-                const int k = ray_rect_first_hit(r, cx, cy, dx, dy, lim);
+                const int k = ray_rect_first_hit(r, ray, lim);
                 if (k) best = k;
             }
         }

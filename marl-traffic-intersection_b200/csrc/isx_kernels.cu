@@ -478,14 +478,14 @@ k_lidar_obs(const Dev d, int mode, int num_groups, int G) {
                 const float cx = s.cx[cb + self], cy = s.cy[cb + self];
                 float sn, cs;
                 sincosf_(s.ch[cb + self] + s.rel[i], &sn, &cs);
-                const float dx = cs, dy = -sn;
+                const Ray ray = make_ray(cx, cy, cs, -sn);
                 bool hit;
-                const int ke = ray_road_event(s.bits, s.skip, cx, cy, dx, dy, &hit);
+                const int ke = ray_road_event(s.bits, s.skip, d.box_lo, d.box_hi, ray, &hit);
                 int best = hit ? ke : 0;
                 int lim = ke - 1;                               // cars only count strictly before the road event
                 for (unsigned long long m = s.cand[a]; m && lim >= 1; m &= m - 1) {
                     const int k = __ffsll((long long)m) - 1;
-                    const int kh = ray_rect_first_hit(s.rect[cb + k], cx, cy, dx, dy, lim);
+                    const int kh = ray_rect_first_hit(s.rect[cb + k], ray, lim);
                     if (kh) { best = kh; lim = kh - 1; }
                 }
                 d.lidar_hit[ga * ISX_MAX_RAYS + i] = (uint8_t)best;

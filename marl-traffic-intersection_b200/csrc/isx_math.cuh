@@ -141,19 +141,28 @@ ISX_HD void sincosf_(float y, float* sinp, float* cosp) {
     const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5,
                  C3 = -0x1.6c087e89a359dp-10, C4 = 0x1.99343027bf8c3p-16;
     const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
-    if (((f2u(y) >> 20) & 0x7ffu) < 0x398u) {   // |y| < 2^-12
-        *sinp = y; *cosp = 1.0f;
-        return;
+    const uint32_t top = (f2u(y) >> 20) & 0x7ffu;
+    double xr;
+    int n, q;
+    if (top < 0x42fu) {
+        // |y| < 120.  glibc branches on |y| < 0.75 first and skips the reduction there; the reduction below
+        // yields n == 0 and xr == y exactly for every |y| < pi/4, so one straight-line path serves both
+        // (keeps the lanes of a warp converged: beam angles span [-2pi, 2pi]).
+        const double x = (double)y;
+        n = (d2i_rz(x * 0x1.45F306DC9C883p+23) + 0x800000) >> 24;
+        xr = fma(-(double)n, 0x1.921FB54442D18p0, x);
+        q = n;
+    } else {
+        int se;
+        if (!sincos_reduce(y, &xr, &n, &se)) {
+            const float nan = y - y;
+            *sinp = nan; *cosp = nan;
+            return;
+        }
+        q = n + se;
     }
-    double xr; int n, se;
-    if (!sincos_reduce(y, &xr, &n, &se)) {
-        const float nan = y - y;
-        *sinp = nan; *cosp = nan;
-        return;
-    }
-    const int q = n + se;
     // sign table {1,-1,-1,1}[q&3]; the second coefficient set (q&2) is the first with c0..c4 negated
-    const double sg = (((q & 3) == 1) || ((q & 3) == 2)) ? -1.0 : 1.0;
+    const double sg = (((q + 1) & 2) != 0) ? -1.0 : 1.0;
     const double xs = xr * sg;
     const double x2 = xr * xr;
     const double x3 = x2 * xs;
@@ -165,11 +174,12 @@ ISX_HD void sincosf_(float y, float* sinp, float* cosp) {
     const double c1v = fma(x2, C1, C0);
     const double sv = fma(x3, S1, xs);
     const double cv = fma(x4, C2, c1v);
-    const float fs = (float)fma(s1v, x5, sv);
+    float fs = (float)fma(s1v, x5, sv);
     float fc = (float)fma(c2v, x6, cv);
     if (q & 2) fc = -fc;
-    if (n & 1) { *sinp = fc; *cosp = fs; }
-    else       { *sinp = fs; *cosp = fc; }
+    if (n & 1) { const float t = fs; fs = fc; fc = t; }
+    if (top < 0x398u) { fs = y; fc = 1.0f; }      // |y| < 2^-12: glibc returns (y, 1) without evaluating anything
+    *sinp = fs; *cosp = fc;
 }
 
 // ---------------------------------------------------------------- tanf

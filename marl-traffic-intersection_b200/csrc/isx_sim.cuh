@@ -263,22 +263,67 @@ ISX_HD int road_skip(const uint8_t* skip, int px, int py) {
     return skip[(v >> 2) * SKIP_DIM + (u >> 2)];
 }
 
+#if defined(ISX_ITER_STATS) && !defined(__CUDA_ARCH__)
+static long long isx_iter_stats_count = 0;   // host-only instrumentation (tools/): march iterations
+#endif
+// Per-ray constants of the march: direction, reciprocals (for the analytic strip exits and the car slabs).
+struct Ray {
+    float cx, cy, dx, dy, inv_dx, inv_dy;
+};
+ISX_HD Ray make_ray(float cx, float cy, float dx, float dy) {
+    Ray r;
+    r.cx = cx; r.cy = cy; r.dx = dx; r.dy = dy;
+    r.inv_dx = (dx != 0.0f) ? 1.0f / dx : 0.0f;
+    r.inv_dy = (dy != 0.0f) ? 1.0f / dy : 0.0f;
+    return r;
+}
+
+// Largest t >= 0 for which  c + d*t  stays inside [lo + 0.01, hi + 0.99]  (pixel in [lo, hi] with 0.01 px slack),
+// given that it is inside at the current sample.  +inf if the coordinate does not move.
+ISX_HD float axis_exit(float c, float d, float inv_d, int lo, int hi) {
+    if (d > 0.0f) return (((float)hi + 0.99f) - c) * inv_d;
+    if (d < 0.0f) return (((float)lo + 0.01f) - c) * inv_d;
+    return INFINITY;
+}
+
 // First road event on a ray: returns k in [1,62] and sets *hit (true = off-road pixel, false = left the
 // screen), or 63 if nothing happens within range.  k = 0 means the origin pixel itself is off screen
-// (Lidar.cpp:38-40 breaks at dist 0).  Sphere-traces with the skip table: a sample whose 4x4 block has
-// skip count j guarantees that the next j samples are on-road and on-screen, so they are not evaluated.
-ISX_HD int ray_road_event(const uint32_t* bits, const uint8_t* skip, float cx, float cy, float dx, float dy, bool* hit) {
+// (Lidar.cpp:38-40 breaks at dist 0).  Exactness-preserving acceleration, two sources of "these samples cannot
+// be events", both verified against the full-resolution map when the tables are built (isx_tables.h):
+//   * skip table: a sample whose 4x4 block has skip count j guarantees the next j samples are on-road, on-screen;
+//   * strip boxes: every pixel of the open vertical strip [box_lo, box_hi] x [0,749] (and of the horizontal one)
+//     is road, so while a ray stays inside a strip — a linear condition in k — nothing can happen.
+// The sample that ends a skip is always tested with the exact pixel arithmetic of Lidar.cpp:34-46.
+ISX_HD int ray_road_event(const uint32_t* bits, const uint8_t* skip, int box_lo, int box_hi, const Ray& r, bool* hit) {
     int px, py;
     *hit = false;
-    ray_pixel(cx, cy, dx, dy, 0, px, py);
+    ray_pixel(r.cx, r.cy, r.dx, r.dy, 0, px, py);
     if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return 0;
     int k = 0;
     while (true) {
-        k += road_skip(skip, px, py) + 1;
+#if defined(ISX_ITER_STATS) && !defined(__CUDA_ARCH__)
+        ++isx_iter_stats_count;
+#endif
+        int u = px - ROAD_HALF; u = u < 0 ? -u : u;
+        int v = py - ROAD_HALF; v = v < 0 ? -v : v;
+        int j = skip[(v >> 2) * SKIP_DIM + (u >> 2)];
+        const bool in_v = (px >= box_lo) && (px <= box_hi);
+        const bool in_h = (py >= box_lo) && (py <= box_hi);
+        if (in_v | in_h) {
+            // exit time of the strip the sample is in: strip walls on one axis, the screen on the other
+            const float tv = in_v ? fminf(axis_exit(r.cx, r.dx, r.inv_dx, box_lo, box_hi), axis_exit(r.cy, r.dy, r.inv_dy, 0, HEIGHT - 1)) : 0.0f;
+            const float th = in_h ? fminf(axis_exit(r.cy, r.dy, r.inv_dy, box_lo, box_hi), axis_exit(r.cx, r.dx, r.inv_dx, 0, WIDTH - 1)) : 0.0f;
+            const float t = fminf(fmaxf(tv, th), 1000.0f);
+            const int kb = (int)(t * 0.25f - 0.01f);          // last sample index certainly inside the strip
+            j = (kb - k > j) ? (kb - k) : j;
+        }
+        k += j + 1;
         if (k > LIDAR_MAX_K) return LIDAR_MAX_K + 1;
-        ray_pixel(cx, cy, dx, dy, k, px, py);
+        ray_pixel(r.cx, r.cy, r.dx, r.dy, k, px, py);
         if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return k;
-        if (!road_bit(bits, px, py)) { *hit = true; return k; }
+        u = px - ROAD_HALF; u = u < 0 ? -u : u;
+        v = py - ROAD_HALF; v = v < 0 ? -v : v;
+        if (!((bits[v * ROAD_WORDS + (u >> 5)] >> (u & 31)) & 1u)) { *hit = true; return k; }
     }
 }
 
@@ -287,7 +332,8 @@ ISX_HD int ray_road_event(const uint32_t* bits, const uint8_t* skip, float cx, f
 // candidates are then checked with the exact integer test, in order.  Only on-screen pixels can be hit
 // (the march breaks off screen first), so the rectangle is clamped to the screen; truncation toward zero
 // maps every value in (-1, 1) to pixel 0, hence the wider lower bound when the clamped edge is 0.
-ISX_HD int ray_rect_first_hit(const PixRect& r, float cx, float cy, float dx, float dy, int kmax) {
+ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
+    const float cx = ray.cx, cy = ray.cy, dx = ray.dx, dy = ray.dy;
     const int x0 = r.x0 < 0 ? 0 : r.x0, x1 = r.x1 > WIDTH - 1 ? WIDTH - 1 : r.x1;
     const int y0 = r.y0 < 0 ? 0 : r.y0, y1 = r.y1 > HEIGHT - 1 ? HEIGHT - 1 : r.y1;
     if (x0 > x1 || y0 > y1) return 0;
@@ -295,7 +341,7 @@ ISX_HD int ray_rect_first_hit(const PixRect& r, float cx, float cy, float dx, fl
     {
         const float lo = (x0 == 0 ? -1.01f : (float)x0 - 0.01f) - cx, hi = ((float)x1 + 1.01f) - cx;
         if (fabsf(dx) > 1e-6f) {
-            const float inv = 1.0f / dx;
+            const float inv = ray.inv_dx;
             float a = lo * inv, b = hi * inv;
             if (a > b) { const float t = a; a = b; b = t; }
             t0 = fmaxf(t0, a); t1 = fminf(t1, b);
@@ -304,7 +350,7 @@ ISX_HD int ray_rect_first_hit(const PixRect& r, float cx, float cy, float dx, fl
     {
         const float lo = (y0 == 0 ? -1.01f : (float)y0 - 0.01f) - cy, hi = ((float)y1 + 1.01f) - cy;
         if (fabsf(dy) > 1e-6f) {
-            const float inv = 1.0f / dy;
+            const float inv = ray.inv_dy;
             float a = lo * inv, b = hi * inv;
             if (a > b) { const float t = a; a = b; b = t; }
             t0 = fmaxf(t0, a); t1 = fminf(t1, b);

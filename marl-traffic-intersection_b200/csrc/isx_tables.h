@@ -139,6 +139,7 @@ inline void lidar_rel_angles(int rays, float* rel) {
 struct RoadTables {
     std::vector<uint32_t> bits;   // ROAD_ROWS x ROAD_WORDS
     std::vector<uint8_t> skip;    // SKIP_DIM x SKIP_DIM
+    int box_lo = 1, box_hi = 0;   // every pixel of [box_lo, box_hi] x [0,749] and of its transpose is road (empty if lo > hi)
 };
 
 // Builds the folded bitmap and skip table from on_road() evaluated at every integer pixel, exactly as the
@@ -173,6 +174,16 @@ inline bool build_road_tables(int lanes, RoadTables* t) {
             }
             clr[(size_t)y * W + x] = c;
         }
+    // strip interior: columns strictly inside the vertical strip are road over the full screen height (the grass
+    // discs only touch the strip walls).  Verified pixel by pixel; an unexpected geometry simply disables the box.
+    {
+        const int rw = lanes * (int)LANE_WIDTH_PX;
+        int lo = WIDTH / 2 - rw + 1, hi = WIDTH / 2 + rw - 1;
+        bool ok = lo <= hi && lo >= 0 && hi < W;
+        for (int y = 0; ok && y < H; ++y)
+            for (int x = lo; ok && x <= hi; ++x) ok = road[(size_t)y * W + x] && road[(size_t)x * W + y];
+        if (ok) { t->box_lo = lo; t->box_hi = hi; } else { t->box_lo = 1; t->box_hi = 0; }
+    }
     t->bits.assign((size_t)ROAD_ROWS * ROAD_WORDS, 0u);
     std::vector<int> fclr((size_t)ROAD_ROWS * ROAD_ROWS, BIG);
     for (int v = 0; v <= ROAD_HALF; ++v)

@@ -1,0 +1,88 @@
+"""Live pinning of the C restatement against the reference's own C++ (oracle/_ref), bit for bit.  Skipped where
+_ref did not travel; tests/test_golden.py covers that case through committed fixtures."""
+import numpy as np
+import pytest
+
+import pyoracle as po
+
+pytestmark = pytest.mark.skipif(not (po.have_ref() and po.have_oracle()), reason="needs oracle/_ref and the C oracle")
+R3 = po.ROUTES_3LANES
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def lockstep(kw, steps, seed, policy=None):
+    r, o = po.RefEnv(seed=seed, **kw), po.OracleEnv(seed=seed, **kw)
+    assert r.n == o.n and (bits(r.obs()) == bits(o.obs())).all()
+    obs = r.obs()
+    hist = np.zeros(6, np.int64)
+    for s in range(steps):
+        a = po.philox_actions(seed, 0, r.tick + 1, r.n) if policy is None else policy(obs)
+        x, y = r.step(a), o.step(a)
+        for k in ("obs", "reward"):
+            assert (bits(x[k]) == bits(y[k])).all(), (s, k)
+        for k in ("done", "status"):
+            assert (x[k] == y[k]).all(), (s, k)
+        for k in ("terminated", "truncated", "agents_alive", "step"):
+            assert x[k] == y[k], (s, k)
+        e1, e2 = r.egos(), o.egos()
+        for f in ("x", "y", "v", "heading", "acc", "steer", "prev_dist", "prev_a0", "prev_a1"):
+            assert (bits(e1[f]) == bits(e2[f])).all(), (s, f)
+        assert (e1["path_index"] == e2["path_index"]).all()
+        for i in range(r.n):
+            assert (r.lidar(i) == o.lidar(i)).all()
+        if kw.get("traffic"):
+            v1, v2 = r.events(), o.events()
+            for f in ("rng_draws", "spawn_route", "spawned", "removed_mask", "npc_count"):
+                assert v1[f] == v2[f], (s, f, v1, v2)
+            n1, n2 = r.npcs(), o.npcs()
+            assert len(n1) == len(n2)
+            for f in ("x", "y", "v", "heading", "steer"):
+                assert (bits(n1[f]) == bits(n2[f])).all(), (s, f)
+            for f in ("path_index", "route", "uid", "intention"):
+                assert (n1[f] == n2[f]).all(), (s, f)
+        for st in x["status"]:
+            hist[st] += 1
+        obs = x["obs"]
+        if x["terminated"] or x["truncated"]:
+            r.reset(); o.reset()
+            obs = r.obs()
+    return hist
+
+
+@pytest.mark.parametrize("kw,steps", [
+    (dict(num_lanes=3, ego_routes=[("IN_6", "OUT_2")]), 2000),
+    (dict(num_lanes=3, ego_routes=[("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")], use_team=True), 2000),
+    (dict(num_lanes=3, ego_routes=[("IN_6", "OUT_2")], traffic=True, density=0.5), 2000),
+    (dict(num_lanes=3, ego_routes=R3[:8]), 500),
+    (dict(num_lanes=3, ego_routes=R3[:8], traffic=True, density=1.0, lidar_rays=72), 500),
+    (dict(num_lanes=2, ego_routes=po.ROUTES_2LANES[:4], traffic=True, density=3.0, respawn=False, max_steps=300), 600),
+    (dict(num_lanes=3, ego_routes=[("IN_6", "OUT_2")], traffic=True, density=30.0), 800),
+])
+def test_lockstep_random_actions(kw, steps):
+    lockstep(kw, steps, seed=1)
+
+
+def test_lockstep_route_following_reaches_success():
+    def pol(obs):
+        steer = np.clip(2.0 * obs[:, 5], -1, 1)
+        thr = np.where(obs[:, 2] * 8.0 < 4.0, 0.35, 0.0)
+        return np.stack([thr, steer], 1).astype(np.float32)
+    h = lockstep(dict(num_lanes=3, ego_routes=[("IN_6", "OUT_2"), ("IN_1", "OUT_4")], max_steps=600, traffic=True, density=2.0), 1200, seed=4, policy=pol)
+    assert h[po.STATUS_NAMES.index("SUCCESS")] > 0
+
+
+def test_error_behaviour_matches():
+    for cls in (po.RefEnv, po.OracleEnv):
+        e = cls(3, [("IN_99", "OUT_1"), ("IN_6", "OUT_2")])      # unknown start: silently no car
+        assert e.n == 1
+        with pytest.raises(IndexError):
+            cls(3, [("IN_6", "OUT_99")])                           # unknown end: out_of_range -> IndexError
+        e = cls(3, [("IN_6", "OUT_2"), ("IN_4", "OUT_8")])
+        a = e.step(np.array([[0.5, 0.1]], np.float32))           # missing actions default to 0
+        assert a["obs"].shape == (2, 127)
+    r, o = po.RefEnv(3, [("IN_6", "OUT_2"), ("IN_4", "OUT_8")]), po.OracleEnv(3, [("IN_6", "OUT_2"), ("IN_4", "OUT_8")])
+    x, y = r.step(np.array([[0.5, 0.1]], np.float32)), o.step(np.array([[0.5, 0.1]], np.float32))
+    assert (bits(x["obs"]) == bits(y["obs"])).all()
