@@ -172,7 +172,8 @@ def main():
         if rank != 0:
             return 0
         threads = os.cpu_count() or 1
-        value, s_per_step, info = cpu_reference_run(samples=K, warmup=min(W, 3), steps_per_sample=25, threads=threads)
+        sps = max(1, min(500, 15000 // K))     # ~30 s of CPU work in total whatever K the driver asks for
+        value, s_per_step, info = cpu_reference_run(samples=K, warmup=min(W, 3), steps_per_sample=sps, threads=threads)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
                 "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(n_gpus, args.envs_per_gpu),
@@ -293,7 +294,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             threads = os.cpu_count() or 1
-            v, _, info = cpu_reference_run(samples=4, warmup=1, steps_per_sample=100, threads=threads)
+            v, _, info = cpu_reference_run(samples=10, warmup=1, steps_per_sample=400, threads=threads)
             cpu_baseline = dict(info, value=v, unit=UNIT)
         except Exception as ex:  # the checker libraries did not travel: report, do not fail the bench
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}

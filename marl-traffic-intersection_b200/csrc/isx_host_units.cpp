@@ -71,23 +71,28 @@ void isxh_lidar(int lanes, int rays, const float* self_pose, const float* others
     lidar_rel_angles(rays, rel.data());
     const float cx = self_pose[0], cy = self_pose[1], h = self_pose[2];
     std::vector<PixRect> rects;
+    std::vector<BeamWindow> wins;
     for (int i = 0; i < n_others; ++i) {
         const float ox = others[3 * i], oy = others[3 * i + 1], oh = others[3 * i + 2];
         if (fabsf(ox - cx) < 1e-3f && fabsf(oy - cy) < 1e-3f && fabsf(oh - h) < 1e-3f) continue;   // Lidar.cpp:58-63
         rects.push_back(car_pixel_rect(ox, oy, oh));
+        wins.push_back(beam_window(rects.back(), cx, cy, h, rays));
     }
     for (int i = 0; i < rays; ++i) {
         float s, c;
         sincosf_(h + rel[i], &s, &c);
         const Ray ray = make_ray(cx, cy, c, -s);
         bool hit;
-        const int ke = ray_road_event(t->bits.data(), t->skip.data(), t->box_lo, t->box_hi, ray, &hit);
+        const RoadView rv{t->bits.data(), t->skip.data(), t->box_lo, t->box_hi};
+        const int ke = ray_road_event(rv, ray, &hit);
         int best = hit ? ke : 0;
         const int kmax = hit ? ke - 1 : ke - 1;     // cars only count strictly before the road event
         if (kmax >= 1) {
-            for (const PixRect& r : rects) {
+            for (size_t q = 0; q < rects.size(); ++q) {
+                const PixRect& r = rects[q];
                 const int lim = best ? best - 1 : kmax;
                 if (lim < 1) break;
+                if (!beam_in_window(wins[q], i, rays)) continue;      // angular pruning, as the kernel does
                 const int k = ray_rect_first_hit(r, ray, lim);
                 if (k) best = k;
             }

@@ -232,14 +232,39 @@ k_dynamics(const Dev d, const float* __restrict__ actions, float dt, float spawn
     float rew = 0.0f;
     int status = ISX_ALIVE;
     bool done = false;
+    if (is_ego && alive) {                             // Car::update, :151-156
+        float thr, st;
+        if (actions) { thr = actions[2 * ai]; st = actions[2 * ai + 1]; }
+        else philox_action(d.seed, genv, tick, (uint32_t)lane, thr, st);
+        car_update(p, steer, acc, thr, st, dt);
+    }
+    {   // Car::update_path_index (:157) with the 50-point window of every ego spread over 32/NP lanes
+        const int NP = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;   // lanes per "row" of egos
+        const int rows = 32 / NP;
+        const int ego = lane & (NP - 1), part = lane / NP;
+        const float ex = __shfl_sync(FULL, p.x, ego), ey = __shfl_sync(FULL, p.y, ego);
+        const int ep = __shfl_sync(FULL, pidx, ego);
+        const int start = ep < 0 ? 0 : ep, end = min(start + 50, PATH_LEN);
+        float best = INFINITY;
+        int bi = start;
+        if (ego < N) {
+            const F2* path = d.route_path + (size_t)ego * PATH_LEN;
+            for (int i = start + part; i < end; i += rows) {
+                const F2 q = path[i];
+                const float dx = q.x - ex, dy = q.y - ey;
+                const float dd = dx * dx + dy * dy;
+                if (dd < best) { best = dd; bi = i; }
+            }
+        }
+        for (int o = NP; o < 32; o <<= 1) {            // first minimum wins: lexicographic (distance, index)
+            const float ob = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (is_ego && alive) pidx = bi;                // lanes 0..N-1 are part 0 of their own ego
+    }
     if (is_ego) {
-        if (alive) {                                   // :151-163
-            float thr, st;
-            if (actions) { thr = actions[2 * ai]; st = actions[2 * ai + 1]; }
-            else philox_action(d.seed, genv, tick, (uint32_t)lane, thr, st);
-            car_update(p, steer, acc, thr, st, dt);
-            const F2* path = d.route_path + (size_t)lane * PATH_LEN;
-            pidx = path_index_update(path, pidx, p.x, p.y);
+        if (alive) {                                   // :159-163
             const RouteMeta m = d.route_meta[lane];
             rew = reward_base(d.rc, p.x, p.y, p.v, acc, steer, m.goal, d.max_progress, pd, pa0, pa1);
             status = ego_self_status(d.lanes, p.x, p.y, p.h, m.goal, m.goal_prev);     // :166-290
@@ -340,11 +365,13 @@ struct LidSmem {
     uint32_t* bits;            // [ROAD_ROWS * ROAD_WORDS]
     float* rel;                // [ISX_MAX_RAYS]
     PixRect* rect;             // [G * CE]   lidar pixel rectangle of every car (egos then NPCs)
-    unsigned long long* cand;  // [LID_AGENTS] per ego: cars a beam can possibly hit
+    int* ncand;                // [LID_AGENTS] per ego: number of cars a beam can possibly hit
+    int* acb;                  // [LID_AGENTS] first car slot of the ego's env
+    int* aself;                // [LID_AGENTS] ego's slot inside its env
+    uint8_t *ccar, *cia, *cspan;   // [LID_AGENTS * CE] candidate car slot, first beam of its window, window span
     float *cx, *cy, *cv, *ch;  // [G * CE]
     int* cintent;              // [G * CE]
     int* ncars;                // [LID_AGENTS]
-    float* feat;               // [LID_AGENTS * 31]
     uint8_t* skip;             // [SKIP_DIM * SKIP_DIM]
     uint8_t* ealive;           // [LID_AGENTS]
 };
@@ -355,32 +382,70 @@ __host__ __device__ inline size_t lid_carve(unsigned char* base, int G, int CE, 
     const size_t o_bits = take(sizeof(uint32_t) * ROAD_ROWS * ROAD_WORDS);
     const size_t o_rel = take(sizeof(float) * ISX_MAX_RAYS);
     const size_t o_rect = take(sizeof(PixRect) * nc);
-    const size_t o_cand = take(sizeof(unsigned long long) * LID_AGENTS);
+    const size_t o_ncand = take(sizeof(int) * LID_AGENTS), o_acb = take(sizeof(int) * LID_AGENTS), o_aself = take(sizeof(int) * LID_AGENTS);
+    const size_t o_ccar = take((size_t)LID_AGENTS * CE), o_cia = take((size_t)LID_AGENTS * CE), o_cspan = take((size_t)LID_AGENTS * CE);
     const size_t o_cx = take(sizeof(float) * nc), o_cy = take(sizeof(float) * nc), o_cv = take(sizeof(float) * nc), o_ch = take(sizeof(float) * nc);
     const size_t o_int = take(sizeof(int) * nc);
     const size_t o_nc = take(sizeof(int) * LID_AGENTS);
-    const size_t o_feat = take(sizeof(float) * LID_AGENTS * 31);
     const size_t o_skip = take(SKIP_DIM * SKIP_DIM);
     const size_t o_alive = take(LID_AGENTS);
     if (s) {
         s->bits = reinterpret_cast<uint32_t*>(base + o_bits); s->rel = reinterpret_cast<float*>(base + o_rel);
-        s->rect = reinterpret_cast<PixRect*>(base + o_rect); s->cand = reinterpret_cast<unsigned long long*>(base + o_cand);
+        s->rect = reinterpret_cast<PixRect*>(base + o_rect);
+        s->ncand = reinterpret_cast<int*>(base + o_ncand); s->acb = reinterpret_cast<int*>(base + o_acb); s->aself = reinterpret_cast<int*>(base + o_aself);
+        s->ccar = base + o_ccar; s->cia = base + o_cia; s->cspan = base + o_cspan;
         s->cx = reinterpret_cast<float*>(base + o_cx); s->cy = reinterpret_cast<float*>(base + o_cy);
         s->cv = reinterpret_cast<float*>(base + o_cv); s->ch = reinterpret_cast<float*>(base + o_ch);
         s->cintent = reinterpret_cast<int*>(base + o_int); s->ncars = reinterpret_cast<int*>(base + o_nc);
-        s->feat = reinterpret_cast<float*>(base + o_feat); s->skip = base + o_skip; s->ealive = base + o_alive;
+        s->skip = base + o_skip; s->ealive = base + o_alive;
     }
     return o;
 }
 
 enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
 
-__global__ void __launch_bounds__(LID_THREADS)
+// Road march for the 32 rays of a warp (must be called by all 32 lanes, converged).  Every lane first takes two
+// accelerated steps of its own ray in lock-step (that finishes ~90% of all rays: mean 1.65 steps/ray); the rays
+// still open are then finished ONE AT A TIME by the whole warp, lane j testing sample k+1+j with the exact pixel
+// arithmetic — so a warp never idles 31 lanes while one grazing ray crawls along a wall.
+__device__ __forceinline__ int warp_road_event(bool active, const RoadView& rv, const Ray& r, bool* hit, int lane) {
+    March m;
+    m.k = 0; m.px = 0; m.py = 0; m.ke = LIDAR_MAX_K + 1; m.done = true; m.hit = false;
+    if (active) march_init(r, m);
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+        if (!m.done) march_step(rv, r, m);
+    unsigned pend = __ballot_sync(FULL, !m.done);
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1;
+        Ray o;
+        o.cx = __shfl_sync(FULL, r.cx, src); o.cy = __shfl_sync(FULL, r.cy, src);
+        o.dx = __shfl_sync(FULL, r.dx, src); o.dy = __shfl_sync(FULL, r.dy, src);
+        const int k0 = __shfl_sync(FULL, m.k, src);
+        int found = LIDAR_MAX_K + 1, fe = 0;
+        for (int base = k0 + 1; base <= LIDAR_MAX_K; base += 32) {
+            const int kk = base + lane;
+            int px, py, e = 0;
+            if (kk <= LIDAR_MAX_K) e = sample_event(rv.bits, o, kk, px, py);
+            const unsigned b = __ballot_sync(FULL, e != 0);
+            if (b) { const int f = __ffs(b) - 1; found = base + f; fe = __shfl_sync(FULL, e, f); break; }
+        }
+        if (lane == src) { m.ke = found; m.hit = (fe == 2); m.done = true; }
+    }
+    *hit = m.hit;
+    return m.ke;
+}
+
+template <int RT>   // RT = beam count known at compile time (72, 96) or 0 = run-time d.R
+__global__ void __launch_bounds__(LID_THREADS, 6)
 k_lidar_obs(const Dev d, int mode, int num_groups, int G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int N = d.N, R = d.R;
+    const int N = d.N, R = RT ? RT : d.R;
     const int CE = N + d.M;
+    const int lane = tid & 31;
+    const RoadView rv{nullptr, nullptr, d.box_lo, d.box_hi};
     LidSmem s;
     lid_carve(smem_raw, G, CE, &s);
     for (int i = tid; i < ROAD_ROWS * ROAD_WORDS; i += LID_THREADS) s.bits[i] = d.road_bits[i];
@@ -417,10 +482,10 @@ k_lidar_obs(const Dev d, int mode, int num_groups, int G) {
             const int nc = s.ncars[g];
             const int cb = g * CE;                 // first car slot of this env
             const Pose me{s.cx[cb + self], s.cy[cb + self], s.cv[cb + self], s.ch[cb + self]};
-            float* f = s.feat + a * 31;
-#pragma unroll
-            for (int i = 0; i < 31; ++i) f[i] = 0.0f;
-            unsigned long long cand = 0;
+            float* orow = d.obs + ((size_t)env0 * N + a) * ISX_OBS_DIM;      // the 31 feature floats go straight to the row
+            int nb = 0;
+            int ncand = 0;
+            s.acb[a] = cb; s.aself[a] = self;
             if (s.ealive[a]) {
                 const int ipx = f2i_rz(me.x), ipy = f2i_rz(me.y);
                 for (int k = 0; k < nc; ++k) {
@@ -429,69 +494,100 @@ k_lidar_obs(const Dev d, int mode, int num_groups, int G) {
                     const PixRect r = s.rect[cb + k];
                     // beams reach at most 248 px (+1 px truncation) from the origin pixel
                     if (r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250) continue;
-                    cand |= 1ull << k;
+                    const BeamWindow w = beam_window(r, me.x, me.y, me.h, R);
+                    const int q = a * CE + ncand++;
+                    s.ccar[q] = (uint8_t)k; s.cia[q] = (uint8_t)w.ia; s.cspan[q] = (uint8_t)w.span;
                 }
                 const F2* path = d.route_path + (size_t)self * PATH_LEN;
                 const int pidx = d.epidx[(env0 + g) * N + self];
-                obs_ego_features(me, path[min(pidx + 10, PATH_LEN - 1)], f);
+                float f6[6];
+                obs_ego_features(me, path[min(pidx + 10, PATH_LEN - 1)], f6);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) orow[i] = f6[i];
                 // five nearest other alive cars, ascending distance, ties by list order (stable, :490)
-                float bd[5]; int bk[5]; int nb = 0;
+                float bd[5]; int bk[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { bd[q] = INFINITY; bk[q] = 0; }
                 for (int k = 0; k < nc; ++k) {
                     if (k == self) continue;
                     if (k < N && !s.ealive[g * N + k]) continue;
                     const float dx = s.cx[cb + k] - me.x, dy = s.cy[cb + k] - me.y;
                     const float dist = fsqrt_rn(dx * dx + dy * dy);
-                    int pos = nb;
-                    while (pos > 0 && dist < bd[pos - 1]) --pos;
-                    if (pos >= 5) continue;
-                    const int last = nb < 5 ? nb : 4;
-                    for (int q = last; q > pos; --q) { bd[q] = bd[q - 1]; bk[q] = bk[q - 1]; }
-                    bd[pos] = dist; bk[pos] = k;
+                    int pos = 0;                       // stable insertion slot = number of kept entries <= dist
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) pos += (bd[q] <= dist) ? 1 : 0;
+#pragma unroll
+                    for (int q = 4; q >= 1; --q) if (q > pos) { bd[q] = bd[q - 1]; bk[q] = bk[q - 1]; }
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) if (q == pos) { bd[q] = dist; bk[q] = k; }
                     if (nb < 5) ++nb;
                 }
-                for (int q = 0; q < nb; ++q) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    if (q >= nb) break;
                     const int k = bk[q];
                     const Pose ot{s.cx[cb + k], s.cy[cb + k], s.cv[cb + k], s.ch[cb + k]};
-                    obs_neighbor_features(me, ot, s.cintent[cb + k], f + 6 + 5 * q);
+                    float f5[5];
+                    obs_neighbor_features(me, ot, s.cintent[cb + k], f5);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) orow[6 + 5 * q + i] = f5[i];
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) orow[i] = 0.0f;
             }
-            s.cand[a] = cand;
+            for (int i = 6 + 5 * nb; i < 31; ++i) orow[i] = 0.0f;          // unused neighbour slots stay zero (:424)
+            s.ncand[a] = ncand;
         }
         __syncthreads();
-        // ---- the 31 feature floats of every ego, written cooperatively
-        for (int t = tid; t < na * 31; t += LID_THREADS) {
-            const int a = t / 31, i = t - a * 31;
-            d.obs[((size_t)env0 * N + a) * ISX_OBS_DIM + i] = s.feat[t];
-        }
-        // ---- beams: one thread per (ego, beam)
-        for (int t = tid; t < na * R; t += LID_THREADS) {
-            const int a = t / R, i = t - a * R;
-            const int g = a / N, self = a - g * N;
+        // ---- beams: one thread per (ego, beam); the trip count is uniform so that warps stay converged for the
+        //      cooperative part of the road march
+        const RoadView road{s.bits, s.skip, rv.box_lo, rv.box_hi};
+        const int items = na * R;
+        for (int t0 = 0; t0 < items; t0 += LID_THREADS) {
+            const int t = t0 + tid;
+            const bool valid = t < items;
+            const int tc = valid ? t : 0;
+            const int a = tc / R, i = tc - a * R;
+            const int cb = s.acb[a], self = s.aself[a];
             const size_t ga = (size_t)env0 * N + a;
-            float out;
-            if (!s.ealive[a]) out = 0.0f;                       // dead ego: all-zero row (:426-429)
-            else if (mode == LIDAR_FROM_HITS) {
-                const int k = d.lidar_hit[ga * ISX_MAX_RAYS + i];
-                out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
-            } else {
-                const int cb = g * CE;
-                const float cx = s.cx[cb + self], cy = s.cy[cb + self];
-                float sn, cs;
-                sincosf_(s.ch[cb + self] + s.rel[i], &sn, &cs);
-                const Ray ray = make_ray(cx, cy, cs, -sn);
-                bool hit;
-                const int ke = ray_road_event(s.bits, s.skip, d.box_lo, d.box_hi, ray, &hit);
-                int best = hit ? ke : 0;
-                int lim = ke - 1;                               // cars only count strictly before the road event
-                for (unsigned long long m = s.cand[a]; m && lim >= 1; m &= m - 1) {
-                    const int k = __ffsll((long long)m) - 1;
-                    const int kh = ray_rect_first_hit(s.rect[cb + k], ray, lim);
-                    if (kh) { best = kh; lim = kh - 1; }
+            const bool alive = valid && s.ealive[a];
+            float out = 0.0f;                                   // dead ego: all-zero row (:426-429)
+            if (mode == LIDAR_FROM_HITS) {
+                if (alive) {
+                    const int k = d.lidar_hit[ga * ISX_MAX_RAYS + i];
+                    out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
                 }
-                d.lidar_hit[ga * ISX_MAX_RAYS + i] = (uint8_t)best;
-                out = (best ? (float)(4 * best) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
+            } else {
+                Ray ray = make_ray(0.0f, 0.0f, 1.0f, 0.0f);
+                if (alive) {
+                    float sn, cs;
+                    sincosf_(s.ch[cb + self] + s.rel[i], &sn, &cs);
+                    ray = make_ray(s.cx[cb + self], s.cy[cb + self], cs, -sn);
+                }
+                bool hit;
+                const int ke = warp_road_event(alive, road, ray, &hit, lane);
+                if (alive) {
+                    int best = hit ? ke : 0;
+                    int lim = ke - 1;                           // cars only count strictly before the road event
+                    const int nc = s.ncand[a];
+                    const int iw = (i == R - 1) ? 0 : i;         // beam R-1 duplicates beam 0
+                    for (int j = 0; j < nc && lim >= 1; ++j) {
+                        const int q = a * CE + j;
+                        const int span = s.cspan[q];
+                        if (span < 255) {                        // angular window of this car (beam_window)
+                            int dlt = iw - (int)s.cia[q];
+                            if (dlt < 0) dlt += R - 1;
+                            if (dlt > span) continue;
+                        }
+                        const int kh = ray_rect_first_hit(s.rect[cb + s.ccar[q]], ray, lim);
+                        if (kh) { best = kh; lim = kh - 1; }
+                    }
+                    d.lidar_hit[ga * ISX_MAX_RAYS + i] = (uint8_t)best;
+                    out = (best ? (float)(4 * best) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
+                }
             }
-            d.obs[ga * ISX_OBS_DIM + 31 + i] = out;
+            if (valid) d.obs[ga * ISX_OBS_DIM + 31 + i] = out;
         }
     }
 }
@@ -565,7 +661,10 @@ cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t 
     const int G = max(1, LID_AGENTS / d.N);
     const int groups = (d.E + G - 1) / G;
     const int grid = min(groups, grid_cap);
-    k_lidar_obs<<<grid, LID_THREADS, lidar_smem_bytes(d), st>>>(d, mode, groups, G);
+    const size_t sm = lidar_smem_bytes(d);
+    if (d.R == 72) k_lidar_obs<72><<<grid, LID_THREADS, sm, st>>>(d, mode, groups, G);
+    else if (d.R == 96) k_lidar_obs<96><<<grid, LID_THREADS, sm, st>>>(d, mode, groups, G);
+    else k_lidar_obs<0><<<grid, LID_THREADS, sm, st>>>(d, mode, groups, G);
     return cudaGetLastError();
 }
 cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st) {
@@ -586,10 +685,16 @@ cudaError_t launch_math_probe(int n, const float* a, const float* b, float* sn, 
     return cudaGetLastError();
 }
 cudaError_t lidar_set_smem_attr(const Dev& d) {
-    return cudaFuncSetAttribute(k_lidar_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lidar_smem_bytes(d));
+    const int b = (int)lidar_smem_bytes(d);
+    cudaError_t e = cudaFuncSetAttribute(k_lidar_obs<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    return e;
 }
 cudaError_t lidar_occupancy(const Dev& d, int* ctas_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs, LID_THREADS, lidar_smem_bytes(d));
+    if (d.R == 72) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<72>, LID_THREADS, lidar_smem_bytes(d));
+    if (d.R == 96) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<96>, LID_THREADS, lidar_smem_bytes(d));
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<0>, LID_THREADS, lidar_smem_bytes(d));
 }
 
 }  // namespace isx

@@ -88,13 +88,22 @@ ISX_HD double dsqrt_rn(double x) {
 }
 
 // ---------------------------------------------------------------- sincosf
-// 4/pi as 24 overlapping 32-bit words (192 bits), for |x| >= 120.
+// 4/pi as 24 overlapping 32-bit words (192 bits), for |x| >= 120.  Table-free (the words are windows of one bit
+// string) so that the rare large-argument path costs no stack frame in the kernels.
 ISX_HD uint32_t inv_pio4_word(int i) {
-    const uint32_t t[24] = {
-        0xa2u, 0xa2f9u, 0xa2f983u, 0xa2f9836eu, 0xf9836e4eu, 0x836e4e44u, 0x6e4e4415u, 0x4e441529u,
-        0x441529fcu, 0x1529fc27u, 0x29fc2757u, 0xfc2757d1u, 0x2757d1f5u, 0x57d1f534u, 0xd1f534ddu, 0xf534ddc0u,
-        0x34ddc0dbu, 0xddc0db62u, 0xc0db6295u, 0xdb629599u, 0x6295993cu, 0x95993c43u, 0x993c4390u, 0x3c439041u};
-    return t[i];
+    // bit string of 4/pi, most significant first, as 27 bytes: a2 f9 83 6e 4e 44 15 29 fc 27 57 d1 f5 34 dd c0 db 62 95 99 3c 43 90 41 ..
+    // word i = bytes [i-3 .. i] of that string (zero-padded on the left)
+    const uint64_t b0 = 0xa2f9836e4e441529ull, b1 = 0xfc2757d1f534ddc0ull, b2 = 0xdb6295993c439041ull;
+    // extract 32 bits ending at byte index i (0-based) of the 24-byte string b0|b1|b2
+    const int end_bit = 8 * (i + 1);          // number of leading bits included
+    // value = (string >> (192 - end_bit)) & 0xffffffff, with the string zero-extended on the left
+    const int sh = 192 - end_bit;             // 0..184
+    uint64_t lo, hi;                          // 128-bit window [hi:lo] = string >> sh (low 64 bits suffice)
+    if (sh >= 128) { lo = b0 >> (sh - 128); }
+    else if (sh >= 64) { const int t = sh - 64; lo = t ? ((b1 >> t) | (b0 << (64 - t))) : b1; }
+    else { lo = sh ? ((b2 >> sh) | (b1 << (64 - sh))) : b2; }
+    (void)hi;
+    return (uint32_t)lo;
 }
 
 // Reduce y to xr in [-pi/4, pi/4] and quadrant n; returns false for inf/nan.  `sgn_extra` is the

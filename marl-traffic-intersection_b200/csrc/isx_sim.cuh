@@ -266,6 +266,15 @@ ISX_HD int road_skip(const uint8_t* skip, int px, int py) {
 #if defined(ISX_ITER_STATS) && !defined(__CUDA_ARCH__)
 static long long isx_iter_stats_count = 0;   // host-only instrumentation (tools/): march iterations
 #endif
+ISX_HD float approx_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 // Per-ray constants of the march: direction, reciprocals (for the analytic strip exits and the car slabs).
 struct Ray {
     float cx, cy, dx, dy, inv_dx, inv_dy;
@@ -273,8 +282,9 @@ struct Ray {
 ISX_HD Ray make_ray(float cx, float cy, float dx, float dy) {
     Ray r;
     r.cx = cx; r.cy = cy; r.dx = dx; r.dy = dy;
-    r.inv_dx = (dx != 0.0f) ? 1.0f / dx : 0.0f;
-    r.inv_dy = (dy != 0.0f) ? 1.0f / dy : 0.0f;
+    // only used for conservative bounds (0.01 px of slack against ~1e-7 relative error): approximate is fine
+    r.inv_dx = (dx != 0.0f) ? approx_rcp(dx) : 0.0f;
+    r.inv_dy = (dy != 0.0f) ? approx_rcp(dy) : 0.0f;
     return r;
 }
 
@@ -286,45 +296,72 @@ ISX_HD float axis_exit(float c, float d, float inv_d, int lo, int hi) {
     return INFINITY;
 }
 
-// First road event on a ray: returns k in [1,62] and sets *hit (true = off-road pixel, false = left the
-// screen), or 63 if nothing happens within range.  k = 0 means the origin pixel itself is off screen
-// (Lidar.cpp:38-40 breaks at dist 0).  Exactness-preserving acceleration, two sources of "these samples cannot
-// be events", both verified against the full-resolution map when the tables are built (isx_tables.h):
+// ---- road march.  State of one ray: the last sample known NOT to be an event (k, px, py), or the result.
+//   done && hit   : off-road pixel at sample ke  (Lidar.cpp:44-48)
+//   done && !hit  : left the screen at sample ke (:38-40), or ke == 63: nothing within range
+//   ke == 0       : the origin pixel itself is off screen (the reference breaks at dist 0)
+struct March {
+    int k, px, py, ke;
+    bool done, hit;
+};
+struct RoadView {
+    const uint32_t* bits;
+    const uint8_t* skip;
+    int box_lo, box_hi;
+};
+
+ISX_HD void march_init(const Ray& r, March& m) {
+    m.k = 0; m.ke = LIDAR_MAX_K + 1; m.done = false; m.hit = false;
+    ray_pixel(r.cx, r.cy, r.dx, r.dy, 0, m.px, m.py);
+    if ((unsigned)m.px >= (unsigned)WIDTH || (unsigned)m.py >= (unsigned)HEIGHT) { m.ke = 0; m.done = true; }
+}
+
+// Exact test of sample k: 0 = nothing, 1 = off screen (march breaks, no hit), 2 = off-road pixel (hit).
+ISX_HD int sample_event(const uint32_t* bits, const Ray& r, int k, int& px, int& py) {
+    ray_pixel(r.cx, r.cy, r.dx, r.dy, k, px, py);
+    if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return 1;
+    int u = px - ROAD_HALF; u = u < 0 ? -u : u;
+    int v = py - ROAD_HALF; v = v < 0 ? -v : v;
+    return ((bits[v * ROAD_WORDS + (u >> 5)] >> (u & 31)) & 1u) ? 0 : 2;
+}
+
+// One accelerated step from a non-event sample.  Exactness-preserving: two sources of "these samples cannot be
+// events", both verified against the full-resolution map when the tables are built (isx_tables.h):
 //   * skip table: a sample whose 4x4 block has skip count j guarantees the next j samples are on-road, on-screen;
 //   * strip boxes: every pixel of the open vertical strip [box_lo, box_hi] x [0,749] (and of the horizontal one)
 //     is road, so while a ray stays inside a strip — a linear condition in k — nothing can happen.
-// The sample that ends a skip is always tested with the exact pixel arithmetic of Lidar.cpp:34-46.
-ISX_HD int ray_road_event(const uint32_t* bits, const uint8_t* skip, int box_lo, int box_hi, const Ray& r, bool* hit) {
-    int px, py;
-    *hit = false;
-    ray_pixel(r.cx, r.cy, r.dx, r.dy, 0, px, py);
-    if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return 0;
-    int k = 0;
-    while (true) {
+// The sample that ends the skip is tested with the exact pixel arithmetic of Lidar.cpp:34-46.
+ISX_HD void march_step(const RoadView& rv, const Ray& r, March& m) {
 #if defined(ISX_ITER_STATS) && !defined(__CUDA_ARCH__)
-        ++isx_iter_stats_count;
+    ++isx_iter_stats_count;
 #endif
-        int u = px - ROAD_HALF; u = u < 0 ? -u : u;
-        int v = py - ROAD_HALF; v = v < 0 ? -v : v;
-        int j = skip[(v >> 2) * SKIP_DIM + (u >> 2)];
-        const bool in_v = (px >= box_lo) && (px <= box_hi);
-        const bool in_h = (py >= box_lo) && (py <= box_hi);
-        if (in_v | in_h) {
-            // exit time of the strip the sample is in: strip walls on one axis, the screen on the other
-            const float tv = in_v ? fminf(axis_exit(r.cx, r.dx, r.inv_dx, box_lo, box_hi), axis_exit(r.cy, r.dy, r.inv_dy, 0, HEIGHT - 1)) : 0.0f;
-            const float th = in_h ? fminf(axis_exit(r.cy, r.dy, r.inv_dy, box_lo, box_hi), axis_exit(r.cx, r.dx, r.inv_dx, 0, WIDTH - 1)) : 0.0f;
-            const float t = fminf(fmaxf(tv, th), 1000.0f);
-            const int kb = (int)(t * 0.25f - 0.01f);          // last sample index certainly inside the strip
-            j = (kb - k > j) ? (kb - k) : j;
-        }
-        k += j + 1;
-        if (k > LIDAR_MAX_K) return LIDAR_MAX_K + 1;
-        ray_pixel(r.cx, r.cy, r.dx, r.dy, k, px, py);
-        if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return k;
-        u = px - ROAD_HALF; u = u < 0 ? -u : u;
-        v = py - ROAD_HALF; v = v < 0 ? -v : v;
-        if (!((bits[v * ROAD_WORDS + (u >> 5)] >> (u & 31)) & 1u)) { *hit = true; return k; }
+    int u = m.px - ROAD_HALF; u = u < 0 ? -u : u;
+    int v = m.py - ROAD_HALF; v = v < 0 ? -v : v;
+    int j = rv.skip[(v >> 2) * SKIP_DIM + (u >> 2)];
+    const bool in_v = (m.px >= rv.box_lo) && (m.px <= rv.box_hi);
+    const bool in_h = (m.py >= rv.box_lo) && (m.py <= rv.box_hi);
+    if (in_v | in_h) {
+        // exit time of the strip the sample is in: strip walls on one axis, the screen on the other
+        const float tv = in_v ? fminf(axis_exit(r.cx, r.dx, r.inv_dx, rv.box_lo, rv.box_hi), axis_exit(r.cy, r.dy, r.inv_dy, 0, HEIGHT - 1)) : 0.0f;
+        const float th = in_h ? fminf(axis_exit(r.cy, r.dy, r.inv_dy, rv.box_lo, rv.box_hi), axis_exit(r.cx, r.dx, r.inv_dx, 0, WIDTH - 1)) : 0.0f;
+        const float t = fminf(fmaxf(tv, th), 1000.0f);
+        const int kb = (int)(t * 0.25f - 0.01f);          // last sample index certainly inside the strip
+        j = (kb - m.k > j) ? (kb - m.k) : j;
     }
+    m.k += j + 1;
+    if (m.k > LIDAR_MAX_K) { m.ke = LIDAR_MAX_K + 1; m.done = true; return; }
+    const int e = sample_event(rv.bits, r, m.k, m.px, m.py);
+    if (e) { m.ke = m.k; m.hit = (e == 2); m.done = true; }
+}
+
+// First road event on a ray (plain sequential form; the kernel runs two lock-step steps per lane and then
+// finishes the few stragglers warp-cooperatively, see isx_kernels.cu).
+ISX_HD int ray_road_event(const RoadView& rv, const Ray& r, bool* hit) {
+    March m;
+    march_init(r, m);
+    while (!m.done) march_step(rv, r, m);
+    *hit = m.hit;
+    return m.ke;
 }
 
 // First sample k in [1, kmax] whose pixel lies inside the rectangle, or 0.  A slab test in real arithmetic
@@ -367,6 +404,46 @@ ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
         if (px >= x0 && px <= x1 && py >= y0 && py <= y1) return k;
     }
     return 0;
+}
+
+// Angular window of beams that can possibly touch a car: the samples that hit the rectangle lie (as real points)
+// inside the rectangle grown by 1.01 px, which sits inside a disc of radius rho about its centre; seen from the
+// ego at distance D > rho that disc spans +-asin(rho/D) <= +-(x + 0.5708 x^3), x = rho/D.  Beam i (i < R-1) points
+// at relative angle -pi + i*2pi/(R-1); beam R-1 duplicates beam 0.  The window is widened by one beam on each
+// side (0.065..0.088 rad, against ~1e-6 rad of rounding).  span = 255 means "every beam".
+struct BeamWindow { int ia, span; };
+ISX_HD BeamWindow beam_window(const PixRect& r, float cx, float cy, float heading, int R) {
+    BeamWindow w;
+    w.ia = 0; w.span = 255;
+    if (R < 4) return w;
+    const float hx = 0.5f * (float)(r.x1 - r.x0) + 1.01f, hy = 0.5f * (float)(r.y1 - r.y0) + 1.01f;
+    const float ccx = 0.5f * (float)(r.x0 + r.x1), ccy = 0.5f * (float)(r.y0 + r.y1);
+    const float X = ccx - cx, Y = ccy - cy;
+    const float D2 = X * X + Y * Y, rho2 = hx * hx + hy * hy;
+    if (!(D2 > rho2 * 1.05f + 1.0f)) return w;
+    const float x = sqrtf(rho2 / D2);
+    const float alpha = x + 0.5708f * x * x * x;
+    const float inv_step = (float)(R - 1) * (1.0f / 6.28318530718f);
+    float phi = atan2f(-Y, X) - heading;                 // approximate libm is fine here: only a conservative bound
+    phi = phi - 6.28318530718f * floorf(phi * (1.0f / 6.28318530718f) + 0.5f);   // to [-pi, pi]
+    const float fc = (phi + 3.14159265359f) * inv_step;
+    const float hw = alpha * inv_step;
+    int ia = (int)floorf(fc - hw) - 1;
+    const int ib = (int)ceilf(fc + hw) + 1;
+    const int span = ib - ia;
+    if (span >= R - 2) return w;
+    const int m = R - 1;
+    ia %= m;
+    if (ia < 0) ia += m;
+    w.ia = ia; w.span = span;
+    return w;
+}
+ISX_HD bool beam_in_window(const BeamWindow& w, int i, int R) {
+    if (w.span >= 255) return true;
+    const int ii = (i == R - 1) ? 0 : i;
+    int dlt = ii - w.ia;
+    if (dlt < 0) dlt += R - 1;
+    return dlt <= w.span;
 }
 
 // ---------------------------------------------------------------- NPC planner pieces (TrafficFlow.cpp:22-196)

@@ -44,6 +44,7 @@ def sass_lines_with_src(kernel_substr):
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    mangled = sys.argv[4] if len(sys.argv) > 4 else kern      # substring of the mangled name (template instances)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], stdout=subprocess.PIPE,
                          stderr=subprocess.DEVNULL, text=True).stdout
     # the report may hold several launches: keep the first block for this kernel
@@ -55,7 +56,7 @@ def main():
     iex, ith = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
     isamp = hdr.index("# Samples")
     stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-    sass = sass_lines_with_src(kern)
+    sass = sass_lines_with_src(mangled)
     body = [r for r in rows[1:] if len(r) > iex and r[iex] != ""]
     if len(body) != len(sass):
         print(f"warning: {len(body)} profiled instructions vs {len(sass)} disassembled", file=sys.stderr)
