@@ -14,6 +14,8 @@
 
 namespace isx {
 size_t lidar_smem_bytes(const Dev& d);
+size_t road_bits_bytes();
+size_t road_skip_bytes();
 cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float spawn_prob, cudaStream_t st);
 cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st);
 cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st);
@@ -164,6 +166,8 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     F2* d_paths; RouteMeta* d_meta; uint32_t* d_bits; uint8_t* d_skip; float* d_rel;
     ALLOC(d_paths, paths.size()); UPLOAD(d_paths, paths.data(), sizeof(F2) * paths.size());
     ALLOC(d_meta, meta.size()); UPLOAD(d_meta, meta.data(), sizeof(RouteMeta) * meta.size());
+    rt.bits.resize(road_bits_bytes() / 4, 0u);        // padded to 16 B multiples for the kernel's vector copy
+    rt.skip.resize(road_skip_bytes(), 0);
     ALLOC(d_bits, rt.bits.size()); UPLOAD(d_bits, rt.bits.data(), sizeof(uint32_t) * rt.bits.size());
     ALLOC(d_skip, rt.skip.size()); UPLOAD(d_skip, rt.skip.data(), rt.skip.size());
     ALLOC(d_rel, rel.size()); UPLOAD(d_rel, rel.data(), sizeof(float) * rel.size());
@@ -181,6 +185,11 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     ALLOC(d.lidar_hit, EN * ISX_MAX_RAYS); ALLOC(d.events, E);
     ALLOC(d.env_stats, E * STAT_SLOTS); ALLOC(d.stats, 16);
     ALLOC(h->d_actions, EN * 2);
+    {
+        float4* rec; int4* rc;
+        ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN); ALLOC(d.ray_counter, 4);
+        d.agent_rec = rec; d.car_rect = rc;
+    }
 #undef ALLOC
 #undef UPLOAD
 

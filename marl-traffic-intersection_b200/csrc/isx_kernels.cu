@@ -1,14 +1,16 @@
 // isx_kernels.cu — the step kernels (sm_100a).
 //
-//   k_dynamics  : one WARP per env.  NPC traffic flow (spawn draw, Gauss-Seidel planner/integrator in list
-//                 order, NPC-NPC SAT, ordered erase) with the warp's lanes spread over ghost-path points /
-//                 other cars / path-window points; then ego physics, reward, status, car-car override,
-//                 bonuses, team mix, respawn and termination with one LANE per ego.
-//                 Replaces TrafficFlow.cpp:317-367 and IntersectionEnv.cpp:137-370.
-//   k_lidar_obs : persistent CTAs; folded road bitmap + skip table staged in shared memory once per CTA;
-//                 one THREAD per (ego, beam): sphere-traced road march + slab/verify against the other cars'
-//                 pixel rectangles; then the 31 ego/neighbour features.  Writes obs rows coalesced.
-//                 Replaces Lidar.cpp:16-90 and IntersectionEnv.cpp:374-390, 418-520.
+//   k_traffic   : one WARP per env.  NPC traffic flow (spawn draw, Gauss-Seidel planner/integrator in list order,
+//                 NPC-NPC SAT, ordered erase), lanes spread over ghost-path points / other NPCs / path-window
+//                 points.  Replaces TrafficFlow.cpp:317-367.  Only launched with traffic flow on.
+//   k_ego       : one LANE per ego, an env = a sub-warp of 2^ceil(log2 N) lanes: physics, reward, status, car-car
+//                 override, bonuses, team mix, respawn, termination.  Replaces IntersectionEnv.cpp:137-370.
+//   k_features  : one THREAD per ego: the 31 ego/neighbour observation features + the per-ego list of cars its
+//                 beams can touch (with angular beam windows).  Replaces IntersectionEnv.cpp:418-508.
+//   k_lidar_obs : one THREAD per (ego, beam), persistent CTAs with the folded road bitmap + skip table in shared
+//                 memory, warps claim 32-beam pieces dynamically: accelerated exact road march + slab/verify
+//                 against the other cars' pixel rectangles.  Writes the lidar part of the obs rows coalesced.
+//                 Replaces Lidar.cpp:16-90 and IntersectionEnv.cpp:374-390, 510-514.
 //
 // No tensor cores: nothing here is a dense contraction.  Build with -fmad=false (see isx_math.cuh).
 #include <cuda_runtime.h>
@@ -20,7 +22,9 @@ namespace isx {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int DYN_WARPS = 4;              // envs per CTA in k_dynamics
 constexpr int LID_THREADS = 256;
-constexpr int LID_AGENTS = 32;            // egos per CTA iteration in k_lidar_obs
+constexpr int WARP_GRAB = 4;              // 32-beam pieces a warp claims per atomic in k_lidar_obs
+constexpr int ROAD_BITS_BYTES = ((ROAD_ROWS * ROAD_WORDS * 4 + 15) / 16) * 16;
+constexpr int ROAD_SKIP_BYTES = ((SKIP_DIM * SKIP_DIM + 15) / 16) * 16;
 
 __device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
@@ -56,9 +60,13 @@ struct NpcSmem {
     uint32_t coll[ISX_MAX_NPC];
 };
 
-// ------------------------------------------------------------------------------------------------ k_dynamics
+// ------------------------------------------------------------------------------------------------ k_traffic
+// NPC traffic flow (TrafficFlow.cpp:317-367), one WARP per env: spawn draw, Gauss-Seidel planner/integrator in list
+// order, NPC-NPC SAT, ordered erase.  The lanes spread over path-window points / other NPCs / ghost-path points.
+// Reads the egos' PRE-step positions (spawn blocking, :244-249), so it runs before k_ego.  Only launched when traffic
+// flow is enabled.
 __global__ void __launch_bounds__(DYN_WARPS * 32)
-k_dynamics(const Dev d, const float* __restrict__ actions, float dt, float spawn_prob) {
+k_traffic(const Dev d, float dt, float spawn_prob) {
     __shared__ NpcSmem sm_all[DYN_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * DYN_WARPS + warp;
@@ -66,10 +74,177 @@ k_dynamics(const Dev d, const float* __restrict__ actions, float dt, float spawn
     NpcSmem& sm = sm_all[warp];
     const int N = d.N;
     const uint32_t genv = (uint32_t)(d.env_base + env);
-    const bool is_ego = lane < N;
-    const int ai = env * N + (is_ego ? lane : 0);
+    int c = d.ncount[env];
+    uint32_t next_uid = d.next_uid[env];
+    const bool reset_now = d.auto_reset && (d.terminated[env] | d.truncated[env]);   // env.py:147-152 after a done step
+    if (reset_now) { c = 0; next_uid = 1; }
+    const uint32_t tick = d.tick[env] + 1;
 
-    // ---- ego state in registers (lane = ego slot)
+    isx_traffic_events evt;
+    evt.rng_draws = 0; evt.spawn_route = -1; evt.spawned = 0; evt.removed_mask = 0; evt.collided_mask = 0; evt.npc_count = 0;
+    uint32_t overflow = 0;
+
+    if (lane < c) {
+        const int ni = env * d.M + lane;
+        sm.x[lane] = d.nx[ni]; sm.y[lane] = d.ny[ni]; sm.v[lane] = d.nv[ni]; sm.h[lane] = d.nh[ni];
+        sm.steer[lane] = d.nsteer[ni]; sm.pidx[lane] = d.npidx[ni]; sm.route[lane] = d.nroute[ni]; sm.uid[lane] = d.nuid[ni];
+    }
+    __syncwarp();
+    // -- spawn draw (:321-329) and try_spawn_traffic_car (:275-315); every lane runs the same stream
+    TrafficStream ts;
+    ts.init(d.seed, genv, tick);
+    if (ts.uniform01() < spawn_prob && d.T > 0) {
+        const int r = (int)ts.below((uint32_t)d.T);
+        evt.spawn_route = r;
+        const RouteMeta m = d.route_meta[N + r];
+        const float md = CAR_LENGTH * 2.5f, md2 = md * md;       // is_spawn_blocked (:240-259)
+        bool blk = false;
+        if (lane < N) {
+            float ex, ey;
+            if (reset_now) { const RouteMeta em = d.route_meta[lane]; ex = em.spawn_x; ey = em.spawn_y; }
+            else { ex = d.ex[env * N + lane]; ey = d.ey[env * N + lane]; }
+            const float dx = ex - m.spawn_x, dy = ey - m.spawn_y;
+            blk = dx * dx + dy * dy < md2;
+        }
+        if (lane < c) { const float dx = sm.x[lane] - m.spawn_x, dy = sm.y[lane] - m.spawn_y; blk = blk || (dx * dx + dy * dy < md2); }
+        if (!__any_sync(FULL, blk)) {
+            if (c < d.M) {
+                if (lane == 0) {
+                    sm.x[c] = m.spawn_x; sm.y[c] = m.spawn_y; sm.v[c] = 0.0f; sm.h[c] = m.spawn_h; sm.steer[c] = 0.0f;
+                    sm.pidx[c] = 0; sm.route[c] = r; sm.uid[c] = next_uid;
+                }
+                next_uid += 1; c += 1; evt.spawned = 1;
+                __syncwarp();
+            } else overflow = 1;                                   // reference list is unbounded; counted
+        }
+    }
+    evt.rng_draws = (int)ts.j;
+
+    // -- NPC controller, sequential in list order: NPC i sees the already-updated state of NPCs < i (:337-344)
+    for (int i = 0; i < c; ++i) {
+        Pose me{sm.x[i], sm.y[i], sm.v[i], sm.h[i]};
+        float msteer = sm.steer[i], macc = 0.0f;
+        const F2* path = d.route_path + (size_t)(N + sm.route[i]) * PATH_LEN;
+        int mp = warp_path_index(path, sm.pidx[i], me.x, me.y, lane);
+        const float steer_cmd = npc_steer_cmd(me, path[min(mp + 12, PATH_LEN - 1)]);
+        float ms, mc;
+        sincosf_nc(me.h, &ms, &mc);
+        const float me_dc = hypotf_nc(me.x - WIDTH * 0.5f, me.y - HEIGHT * 0.5f);
+        float fc = 1e9f;
+        int flags = 0;
+        if (lane < c && lane != i) {
+            const Pose ot{sm.x[lane], sm.y[lane], sm.v[lane], sm.h[lane]};
+            fc = npc_front_candidate(me, ot, ms, mc);
+            flags = npc_pair_flags(me, ot, ms, mc, me_dc, i < lane);
+        }
+        const float thr0 = npc_cruise_throttle(me.v, warp_min_f(fc));
+        const unsigned elig = __ballot_sync(FULL, flags & 1);
+        const unsigned yld = __ballot_sync(FULL, flags & 2);
+        bool conflict = false;
+        float min_conf = 1e9f;
+        if (elig) {                                                // ghost-path scan (:91-185), 32 points per pass
+            const float safe_sq = (CAR_WIDTH * 2.0f) * (CAR_WIDTH * 2.0f);
+            const int s1 = min(mp + 120, PATH_LEN);
+            for (int base = mp; base < s1 && !conflict; base += 32) {
+                const int g = base + lane;
+                bool hit = false;
+                float dtc = 0.0f;
+                if (g < s1) {
+                    const F2 gp = path[g];
+                    unsigned near_yield = 0, near_any = 0;
+                    for (unsigned m = elig; m; m &= m - 1) {
+                        const int o = __ffs(m) - 1;
+                        const float dx = sm.x[o] - gp.x, dy = sm.y[o] - gp.y;
+                        if (dx * dx + dy * dy < safe_sq) { near_any = 1; near_yield |= (yld >> o) & 1u; }
+                    }
+                    if (near_any) {
+                        dtc = hypotf_nc(gp.x - me.x, gp.y - me.y);
+                        hit = near_yield || (dtc < 15.0f);
+                    }
+                }
+                const unsigned hb = __ballot_sync(FULL, hit);
+                if (hb) { conflict = true; min_conf = __shfl_sync(FULL, dtc, __ffs(hb) - 1); }
+            }
+        }
+        const float thr = npc_final_throttle(thr0, conflict, min_conf);
+        car_update(me, msteer, macc, thr, steer_cmd, dt);
+        mp = warp_path_index(path, mp, me.x, me.y, lane);
+        __syncwarp();
+        if (lane == 0) { sm.x[i] = me.x; sm.y[i] = me.y; sm.v[i] = me.v; sm.h[i] = me.h; sm.steer[i] = msteer; sm.pidx[i] = mp; }
+        __syncwarp();
+    }
+
+    // -- NPC-NPC collisions (:347-356): lane j tests the pair (i, j), j > i
+    unsigned alive_m = c >= 32 ? FULL : ((1u << c) - 1u);
+    const unsigned all_m = alive_m;
+    for (int i = 0; i + 1 < c; ++i) {
+        bool hit = false;
+        if (lane > i && lane < c) hit = cars_collide(sm.x[i], sm.y[i], sm.h[i], sm.x[lane], sm.y[lane], sm.h[lane]);
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if ((alive_m >> i) & 1u) {
+            const unsigned m = hm & alive_m;
+            if (m) alive_m &= ~(m | (1u << i));
+        }
+    }
+    // -- ordered erase of dead / arrived / out-of-screen (:359-366)
+    bool rem = false;
+    float mx = 0, my = 0, mv = 0, mh = 0, mst = 0; int mpi = 0, mr = 0; uint32_t mu = 0;
+    if (lane < c) {
+        mx = sm.x[lane]; my = sm.y[lane]; mv = sm.v[lane]; mh = sm.h[lane]; mst = sm.steer[lane];
+        mpi = sm.pidx[lane]; mr = sm.route[lane]; mu = sm.uid[lane];
+        const F2 goal = d.route_meta[N + mr].goal;
+        const bool arrived = hypotf_nc(mx - goal.x, my - goal.y) < 20.0f;
+        const bool oos = mx < -100.0f || mx > (float)WIDTH + 100.0f || my < -100.0f || my > (float)HEIGHT + 100.0f;
+        rem = !((alive_m >> lane) & 1u) || arrived || oos;
+    }
+    const unsigned rem_m = __ballot_sync(FULL, rem);
+    evt.removed_mask = rem_m;
+    evt.collided_mask = all_m & ~alive_m;
+    const unsigned keep_m = all_m & ~rem_m;
+    if (lane < c && !rem) {
+        const int pos = __popc(keep_m & ((1u << lane) - 1u));
+        const int ni = env * d.M + pos;
+        d.nx[ni] = mx; d.ny[ni] = my; d.nv[ni] = mv; d.nh[ni] = mh; d.nsteer[ni] = mst;
+        d.npidx[ni] = mpi; d.nroute[ni] = mr; d.nuid[ni] = mu;
+        // lidar pixel rectangle of this NPC for k_features / k_lidar_obs
+        reinterpret_cast<PixRect*>(d.car_rect)[(size_t)env * (N + d.M) + N + pos] = car_pixel_rect(mx, my, mh);
+    }
+    c = __popc(keep_m);
+    evt.npc_count = c;
+    if (lane == 0) { d.ncount[env] = c; d.next_uid[env] = next_uid; d.events[env] = evt; }
+    {
+        uint32_t* st = d.env_stats + (size_t)env * STAT_SLOTS;
+        uint32_t inc = 0;
+        if (lane == ST_SPAWNED) inc = (uint32_t)evt.spawned;
+        else if (lane == ST_REMOVED) inc = (uint32_t)__popc(evt.removed_mask);
+        else if (lane == ST_COLLIDED) inc = (uint32_t)__popc(evt.collided_mask);
+        else if (lane == ST_OVERFLOW) inc = overflow;
+        if (inc) st[lane] += inc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_ego
+// Ego physics, reward, status, car-car override, bonuses, team mix, respawn, termination (IntersectionEnv.cpp:137-370).
+// One LANE per ego; an env occupies a sub-warp of NP = 2^ceil(log2 N) lanes, so a warp serves 32/NP envs and the
+// lanes stay busy (8 egos/env -> 4 envs per warp).  All exchanges between the egos of an env are sub-warp shuffles /
+// ballot slices.  Runs after k_traffic (ego-NPC collisions see the post-update NPCs, :307-317).
+template <int NP>
+__global__ void __launch_bounds__(128)
+k_ego(const Dev d, const float* __restrict__ actions, float dt) {
+    constexpr int EPW = 32 / NP;                                  // envs per warp
+    constexpr unsigned LOW = NP == 32 ? 0xffffffffu : ((1u << NP) - 1u);
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / NP, a = lane % NP;
+    const int env_raw = wg * EPW + sub;
+    const bool env_ok = env_raw < d.E;
+    const int env = env_ok ? env_raw : d.E - 1;
+    const int N = d.N;
+    const bool is_ego = env_ok && a < N;
+    const int ai = env * N + (a < N ? a : 0);
+    const int shift = sub * NP;
+    const uint32_t genv = (uint32_t)(d.env_base + env);
+
     Pose p{0, 0, 0, 0};
     float steer = 0, acc = 0, pd = 0, pa0 = 0, pa1 = 0;
     int pidx = 0;
@@ -80,220 +255,62 @@ k_dynamics(const Dev d, const float* __restrict__ actions, float dt, float spawn
         pidx = d.epidx[ai]; alive = d.ealive[ai] != 0;
     }
     int step_count = d.step_count[env];
-    int c = d.traffic ? d.ncount[env] : 0;
-    uint32_t next_uid = d.next_uid[env];
     uint32_t resets = 0;
-
     // ---- auto-reset: what a caller of env.py does after terminated|truncated (reset(), env.py:147-152)
     if (d.auto_reset && (d.terminated[env] | d.truncated[env])) {
         if (is_ego) {
-            const RouteMeta m = d.route_meta[lane];
+            const RouteMeta m = d.route_meta[a];
             p.x = m.spawn_x; p.y = m.spawn_y; p.v = 0.0f; p.h = m.spawn_h;
             steer = 0; acc = 0; pd = 0; pa0 = 0; pa1 = 0; pidx = 0; alive = true;
         }
-        step_count = 0; c = 0; next_uid = 1; resets = 1;
+        step_count = 0; resets = 1;
     }
     step_count += 1;                               // IntersectionEnv.cpp:137
     const uint32_t tick = d.tick[env] + 1;
+    const int c = d.traffic ? d.ncount[env] : 0;   // NPCs after this step's traffic update
 
-    isx_traffic_events evt;
-    evt.rng_draws = 0; evt.spawn_route = -1; evt.spawned = 0; evt.removed_mask = 0; evt.collided_mask = 0; evt.npc_count = 0;
-    uint32_t overflow = 0;
-
-    // ================================================================ traffic flow (TrafficFlow.cpp:317-367)
-    if (d.traffic) {
-        if (lane < c) {
-            const int ni = env * d.M + lane;
-            sm.x[lane] = d.nx[ni]; sm.y[lane] = d.ny[ni]; sm.v[lane] = d.nv[ni]; sm.h[lane] = d.nh[ni];
-            sm.steer[lane] = d.nsteer[ni]; sm.pidx[lane] = d.npidx[ni]; sm.route[lane] = d.nroute[ni]; sm.uid[lane] = d.nuid[ni];
-        }
-        __syncwarp();
-        // -- spawn draw (:321-329) and try_spawn_traffic_car (:275-315); every lane runs the same stream
-        TrafficStream ts;
-        ts.init(d.seed, genv, tick);
-        if (ts.uniform01() < spawn_prob && d.T > 0) {
-            const int r = (int)ts.below((uint32_t)d.T);
-            evt.spawn_route = r;
-            const RouteMeta m = d.route_meta[N + r];
-            const float md = CAR_LENGTH * 2.5f, md2 = md * md;       // is_spawn_blocked (:240-259)
-            bool blk = false;
-            if (is_ego) { const float dx = p.x - m.spawn_x, dy = p.y - m.spawn_y; blk = dx * dx + dy * dy < md2; }
-            if (lane < c) { const float dx = sm.x[lane] - m.spawn_x, dy = sm.y[lane] - m.spawn_y; blk = blk || (dx * dx + dy * dy < md2); }
-            if (!__any_sync(FULL, blk)) {
-                if (c < d.M) {
-                    if (lane == 0) {
-                        sm.x[c] = m.spawn_x; sm.y[c] = m.spawn_y; sm.v[c] = 0.0f; sm.h[c] = m.spawn_h; sm.steer[c] = 0.0f;
-                        sm.pidx[c] = 0; sm.route[c] = r; sm.uid[c] = next_uid;
-                    }
-                    next_uid += 1; c += 1; evt.spawned = 1;
-                    __syncwarp();
-                } else overflow = 1;                                   // reference list is unbounded; counted
-            }
-        }
-        evt.rng_draws = (int)ts.j;
-
-        // -- NPC controller, sequential in list order: NPC i sees the already-updated state of NPCs < i (:337-344)
-        for (int i = 0; i < c; ++i) {
-            Pose me{sm.x[i], sm.y[i], sm.v[i], sm.h[i]};
-            float msteer = sm.steer[i], macc = 0.0f;
-            const F2* path = d.route_path + (size_t)(N + sm.route[i]) * PATH_LEN;
-            int mp = warp_path_index(path, sm.pidx[i], me.x, me.y, lane);
-            const float steer_cmd = npc_steer_cmd(me, path[min(mp + 12, PATH_LEN - 1)]);
-            float ms, mc;
-            sincosf_(me.h, &ms, &mc);
-            const float me_dc = hypotf_(me.x - WIDTH * 0.5f, me.y - HEIGHT * 0.5f);
-            float fc = 1e9f;
-            int flags = 0;
-            Pose ot{0, 0, 0, 0};
-            if (lane < c && lane != i) {
-                ot = Pose{sm.x[lane], sm.y[lane], sm.v[lane], sm.h[lane]};
-                fc = npc_front_candidate(me, ot, ms, mc);
-                flags = npc_pair_flags(me, ot, ms, mc, me_dc, i < lane);
-            }
-            const float thr0 = npc_cruise_throttle(me.v, warp_min_f(fc));
-            const unsigned elig = __ballot_sync(FULL, flags & 1);
-            const unsigned yld = __ballot_sync(FULL, flags & 2);
-            bool conflict = false;
-            float min_conf = 1e9f;
-            if (elig) {                                                // ghost-path scan (:91-185), 32 points per pass
-                const float safe_sq = (CAR_WIDTH * 2.0f) * (CAR_WIDTH * 2.0f);
-                const int s1 = min(mp + 120, PATH_LEN);
-                for (int base = mp; base < s1 && !conflict; base += 32) {
-                    const int g = base + lane;
-                    bool hit = false;
-                    float dtc = 0.0f;
-                    if (g < s1) {
-                        const F2 gp = path[g];
-                        unsigned near_yield = 0, near_any = 0;
-                        for (unsigned m = elig; m; m &= m - 1) {
-                            const int o = __ffs(m) - 1;
-                            const float dx = sm.x[o] - gp.x, dy = sm.y[o] - gp.y;
-                            if (dx * dx + dy * dy < safe_sq) { near_any = 1; near_yield |= (yld >> o) & 1u; }
-                        }
-                        if (near_any) {
-                            dtc = hypotf_(gp.x - me.x, gp.y - me.y);
-                            hit = near_yield || (dtc < 15.0f);
-                        }
-                    }
-                    const unsigned hb = __ballot_sync(FULL, hit);
-                    if (hb) { conflict = true; min_conf = __shfl_sync(FULL, dtc, __ffs(hb) - 1); }
-                }
-            }
-            const float thr = npc_final_throttle(thr0, conflict, min_conf);
-            car_update(me, msteer, macc, thr, steer_cmd, dt);
-            mp = warp_path_index(path, mp, me.x, me.y, lane);
-            __syncwarp();
-            if (lane == 0) { sm.x[i] = me.x; sm.y[i] = me.y; sm.v[i] = me.v; sm.h[i] = me.h; sm.steer[i] = msteer; sm.pidx[i] = mp; }
-            __syncwarp();
-        }
-
-        // -- NPC-NPC collisions (:347-356): lane j tests the pair (i, j), j > i
-        unsigned alive_m = c >= 32 ? FULL : ((1u << c) - 1u);
-        const unsigned all_m = alive_m;
-        for (int i = 0; i + 1 < c; ++i) {
-            bool hit = false;
-            if (lane > i && lane < c) hit = cars_collide(sm.x[i], sm.y[i], sm.h[i], sm.x[lane], sm.y[lane], sm.h[lane]);
-            const unsigned hm = __ballot_sync(FULL, hit);
-            if ((alive_m >> i) & 1u) {
-                const unsigned m = hm & alive_m;
-                if (m) alive_m &= ~(m | (1u << i));
-            }
-        }
-        // -- ordered erase of dead / arrived / out-of-screen (:359-366)
-        bool rem = false;
-        float mx = 0, my = 0, mv = 0, mh = 0, mst = 0; int mpi = 0, mr = 0; uint32_t mu = 0;
-        if (lane < c) {
-            mx = sm.x[lane]; my = sm.y[lane]; mv = sm.v[lane]; mh = sm.h[lane]; mst = sm.steer[lane];
-            mpi = sm.pidx[lane]; mr = sm.route[lane]; mu = sm.uid[lane];
-            const F2 goal = d.route_meta[N + mr].goal;
-            const bool arrived = hypotf_(mx - goal.x, my - goal.y) < 20.0f;
-            const bool oos = mx < -100.0f || mx > (float)WIDTH + 100.0f || my < -100.0f || my > (float)HEIGHT + 100.0f;
-            rem = !((alive_m >> lane) & 1u) || arrived || oos;
-        }
-        const unsigned rem_m = __ballot_sync(FULL, rem);
-        evt.removed_mask = rem_m;
-        evt.collided_mask = all_m & ~alive_m;
-        const unsigned keep_m = all_m & ~rem_m;
-        __syncwarp();
-        if (lane < c && !rem) {
-            const int pos = __popc(keep_m & ((1u << lane) - 1u));
-            sm.x[pos] = mx; sm.y[pos] = my; sm.v[pos] = mv; sm.h[pos] = mh; sm.steer[pos] = mst;
-            sm.pidx[pos] = mpi; sm.route[pos] = mr; sm.uid[pos] = mu;
-            const int ni = env * d.M + pos;
-            d.nx[ni] = mx; d.ny[ni] = my; d.nv[ni] = mv; d.nh[ni] = mh; d.nsteer[ni] = mst;
-            d.npidx[ni] = mpi; d.nroute[ni] = mr; d.nuid[ni] = mu;
-        }
-        c = __popc(keep_m);
-        evt.npc_count = c;
-        __syncwarp();
-    }
-
-    // ================================================================ egos (IntersectionEnv.cpp:144-370)
     float rew = 0.0f;
     int status = ISX_ALIVE;
     bool done = false;
-    if (is_ego && alive) {                             // Car::update, :151-156
-        float thr, st;
-        if (actions) { thr = actions[2 * ai]; st = actions[2 * ai + 1]; }
-        else philox_action(d.seed, genv, tick, (uint32_t)lane, thr, st);
-        car_update(p, steer, acc, thr, st, dt);
-    }
-    {   // Car::update_path_index (:157) with the 50-point window of every ego spread over 32/NP lanes
-        const int NP = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;   // lanes per "row" of egos
-        const int rows = 32 / NP;
-        const int ego = lane & (NP - 1), part = lane / NP;
-        const float ex = __shfl_sync(FULL, p.x, ego), ey = __shfl_sync(FULL, p.y, ego);
-        const int ep = __shfl_sync(FULL, pidx, ego);
-        const int start = ep < 0 ? 0 : ep, end = min(start + 50, PATH_LEN);
-        float best = INFINITY;
-        int bi = start;
-        if (ego < N) {
-            const F2* path = d.route_path + (size_t)ego * PATH_LEN;
-            for (int i = start + part; i < end; i += rows) {
-                const F2 q = path[i];
-                const float dx = q.x - ex, dy = q.y - ey;
-                const float dd = dx * dx + dy * dy;
-                if (dd < best) { best = dd; bi = i; }
-            }
-        }
-        for (int o = NP; o < 32; o <<= 1) {            // first minimum wins: lexicographic (distance, index)
-            const float ob = __shfl_xor_sync(FULL, best, o);
-            const int oi = __shfl_xor_sync(FULL, bi, o);
-            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (is_ego && alive) pidx = bi;                // lanes 0..N-1 are part 0 of their own ego
-    }
     if (is_ego) {
-        if (alive) {                                   // :159-163
-            const RouteMeta m = d.route_meta[lane];
+        if (alive) {                               // :151-163
+            float thr, st;
+            if (actions) { thr = actions[2 * ai]; st = actions[2 * ai + 1]; }
+            else philox_action(d.seed, genv, tick, (uint32_t)a, thr, st);
+            car_update(p, steer, acc, thr, st, dt);
+            pidx = path_index_update(d.route_path + (size_t)a * PATH_LEN, pidx, p.x, p.y);
+            const RouteMeta m = d.route_meta[a];
             rew = reward_base(d.rc, p.x, p.y, p.v, acc, steer, m.goal, d.max_progress, pd, pa0, pa1);
             status = ego_self_status(d.lanes, p.x, p.y, p.h, m.goal, m.goal_prev);     // :166-290
             done = status != ISX_ALIVE;
         } else { status = ISX_DEAD; done = true; }
     }
     // -- car-car override (:293-318)
-    unsigned cmask = 0;                                // bit j: ego `lane` collides with ego j > lane
+    unsigned cmask = 0;                            // bit j: ego a collides with ego j > a (sub-warp numbering)
     for (int dlt = 1; dlt < N; ++dlt) {
-        const float ox = __shfl_down_sync(FULL, p.x, dlt), oy = __shfl_down_sync(FULL, p.y, dlt), oh = __shfl_down_sync(FULL, p.h, dlt);
-        if (is_ego && lane + dlt < N && cars_collide(p.x, p.y, p.h, ox, oy, oh)) cmask |= 1u << (lane + dlt);
+        const float ox = __shfl_down_sync(FULL, p.x, dlt, NP), oy = __shfl_down_sync(FULL, p.y, dlt, NP), oh = __shfl_down_sync(FULL, p.h, dlt, NP);
+        if (is_ego && a + dlt < N && cars_collide(p.x, p.y, p.h, ox, oy, oh)) cmask |= 1u << (a + dlt);
     }
     bool npc_hit = false;
-    if (d.traffic && is_ego) {
-        for (int k = 0; k < c && !npc_hit; ++k) npc_hit = cars_collide(p.x, p.y, p.h, sm.x[k], sm.y[k], sm.h[k]);
+    if (is_ego) {
+        for (int k = 0; k < c && !npc_hit; ++k) {
+            const int ni = env * d.M + k;
+            npc_hit = cars_collide(p.x, p.y, p.h, d.nx[ni], d.ny[ni], d.nh[ni]);
+        }
     }
     {
-        const unsigned alive_m = __ballot_sync(FULL, is_ego && alive);
-        unsigned done_m = __ballot_sync(FULL, is_ego && done);
-        const unsigned npc_m = __ballot_sync(FULL, npc_hit);
+        const unsigned alive_m = (__ballot_sync(FULL, is_ego && alive) >> shift) & LOW;
+        unsigned done_m = (__ballot_sync(FULL, is_ego && done) >> shift) & LOW;
+        const unsigned npc_m = (__ballot_sync(FULL, npc_hit) >> shift) & LOW;
         unsigned crash_m = 0;
         for (int i = 0; i < N; ++i) {
-            const unsigned ci = __shfl_sync(FULL, cmask, i);
+            const unsigned ci = __shfl_sync(FULL, cmask, i, NP);
             if (!((alive_m >> i) & 1u) || ((done_m >> i) & 1u)) continue;
             const unsigned m = ci & alive_m & ~done_m;
             if (m) { done_m |= m | (1u << i); crash_m |= m | (1u << i); }
             if ((npc_m >> i) & 1u) { done_m |= 1u << i; crash_m |= 1u << i; }
         }
-        if ((crash_m >> lane) & 1u) { done = true; status = ISX_CRASH_CAR; }
+        if (is_ego && ((crash_m >> a) & 1u)) { done = true; status = ISX_CRASH_CAR; }
     }
     // -- terminal bonuses (:321-326)
     if (is_ego && done) {
@@ -304,18 +321,18 @@ k_dynamics(const Dev d, const float* __restrict__ actions, float dt, float spawn
     // -- team mix (:329-336): sum in index order, then blend
     if (d.use_team && N > 0) {
         float avg = 0.0f;
-        for (int i = 0; i < N; ++i) avg += __shfl_sync(FULL, rew, i);
+        for (int i = 0; i < N; ++i) avg += __shfl_sync(FULL, rew, i, NP);
         avg /= (float)N;
         rew = (1.0f - d.rc.alpha) * rew + d.rc.alpha * avg;
     }
     // -- respawn / termination (:339-370)
-    const unsigned alive_m = __ballot_sync(FULL, is_ego && alive);
-    const unsigned done_m = __ballot_sync(FULL, is_ego && done);
-    const unsigned succ_m = __ballot_sync(FULL, is_ego && alive && done && status == ISX_SUCCESS);
+    const unsigned alive_m = (__ballot_sync(FULL, is_ego && alive) >> shift) & LOW;
+    const unsigned done_m = (__ballot_sync(FULL, is_ego && done) >> shift) & LOW;
+    const unsigned succ_m = (__ballot_sync(FULL, is_ego && alive && done && status == ISX_SUCCESS) >> shift) & LOW;
     bool term = false;
     if (d.respawn) {
         if (is_ego && alive && done && (status == ISX_CRASH_CAR || status == ISX_CRASH_WALL || status == ISX_CRASH_LINE)) {
-            const RouteMeta m = d.route_meta[lane];           // Car::respawn (Car.cpp:76-84)
+            const RouteMeta m = d.route_meta[a];                  // Car::respawn (Car.cpp:76-84)
             p.x = m.spawn_x; p.y = m.spawn_y; p.v = 0.0f; p.h = m.spawn_h;
             pidx = 0; pd = 0.0f; pa0 = 0.0f; pa1 = 0.0f; acc = 0.0f; steer = 0.0f;
         }
@@ -330,80 +347,121 @@ k_dynamics(const Dev d, const float* __restrict__ actions, float dt, float spawn
         d.esteer[ai] = steer; d.eacc[ai] = acc; d.epd[ai] = pd; d.epa0[ai] = pa0; d.epa1[ai] = pa1;
         d.epidx[ai] = pidx; d.ealive[ai] = alive ? 1 : 0;
         d.reward[ai] = rew; d.done[ai] = done ? 1 : 0; d.status[ai] = (uint8_t)status;
+        // lidar pixel rectangle of the (possibly respawned) ego for k_features / k_lidar_obs
+        reinterpret_cast<PixRect*>(d.car_rect)[(size_t)env * (N + d.M) + a] = car_pixel_rect(p.x, p.y, p.h);
     }
-    if (lane == 0) {
-        d.step_count[env] = step_count; d.tick[env] = tick; d.next_uid[env] = next_uid;
+    if (env_ok && a == 0) {
+        d.step_count[env] = step_count; d.tick[env] = tick;
         d.terminated[env] = term ? 1 : 0; d.truncated[env] = trunc ? 1 : 0; d.agents_alive[env] = __popc(alive_m);
-        if (d.traffic) d.ncount[env] = c;
-        d.events[env] = evt;
+        if (!d.traffic && resets) { d.ncount[env] = 0; }
     }
     // ---- per-env counters (no atomics; reduced on demand by k_reduce_stats)
     {
         double rs = is_ego ? (double)rew : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(FULL, rs, o);
-        uint32_t* st = d.env_stats + (size_t)env * STAT_SLOTS;
+        for (int o = NP / 2; o > 0; o >>= 1) rs += __shfl_xor_sync(FULL, rs, o, NP);
         unsigned hist[6];
 #pragma unroll
-        for (int s = 0; s < 6; ++s) hist[s] = __popc(__ballot_sync(FULL, is_ego && status == s));
-        uint32_t inc = 0;
-        if (lane < 6) inc = hist[lane];
-        else if (lane == ST_SPAWNED) inc = (uint32_t)evt.spawned;
-        else if (lane == ST_REMOVED) inc = (uint32_t)__popc(evt.removed_mask);
-        else if (lane == ST_COLLIDED) inc = (uint32_t)__popc(evt.collided_mask);
-        else if (lane == ST_OVERFLOW) inc = overflow;
-        else if (lane == ST_RESETS) inc = resets;
-        else if (lane == ST_STEPS) inc = (uint32_t)N;
-        if (lane < 14) { if (inc) st[lane] += inc; }
-        else if (lane == 14) { double* ps = reinterpret_cast<double*>(st + ST_RSUM); *ps += rs; }
+        for (int s6 = 0; s6 < 6; ++s6) hist[s6] = __popc((__ballot_sync(FULL, is_ego && status == s6) >> shift) & LOW);
+        if (env_ok && a == 0) {
+            uint32_t* st = d.env_stats + (size_t)env * STAT_SLOTS;
+#pragma unroll
+            for (int s6 = 0; s6 < 6; ++s6) if (hist[s6]) st[ST_HIST0 + s6] += hist[s6];
+            if (resets) st[ST_RESETS] += resets;
+            st[ST_STEPS] += (uint32_t)N;
+            double* ps = reinterpret_cast<double*>(st + ST_RSUM);
+            *ps += rs;
+        }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ k_features
+// One THREAD per ego.  Writes the 31 ego / neighbour features of its obs row (IntersectionEnv.cpp:431-508) and
+// prepares the beam kernel's inputs: the ego's pose record, the lidar pixel rectangle of every car of the env
+// (Lidar.cpp:65-78 as integer bounds) and, per ego, the packed list of cars a beam can possibly touch together with
+// the angular beam window of each (beam_window).  Cheap (<2% of the step): thread-per-ego, no shared memory.
+enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
+struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE, or -1 for a dead ego
+
+__global__ void __launch_bounds__(128)
+k_features(const Dev d, int mode) {
+    const int ga = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = d.N, R = d.R;
+    if (ga == 0) *d.ray_counter = 0u;              // work counter of the k_lidar_obs launch that follows in the stream
+    if (ga >= d.E * N) return;
+    const int env = ga / N, self = ga - env * N;
+    const int CE = N + d.M;
+    const int nn = d.traffic ? d.ncount[env] : 0;
+    const int nc = N + nn;
+    const Pose me{d.ex[ga], d.ey[ga], d.ev[ga], d.eh[ga]};
+    const bool alive = d.ealive[ga] != 0;
+    AgentRec rec;
+    rec.x = me.x; rec.y = me.y; rec.h = me.h; rec.rect_base = alive ? env * CE : -1;
+    reinterpret_cast<AgentRec*>(d.agent_rec)[ga] = rec;
+    float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
+    if (!alive) {                                  // dead ego: all-zero row (:426-429)
+        for (int i = 0; i < 31; ++i) orow[i] = 0.0f;
+        d.cand_n[ga] = 0;
+        return;
+    }
+    float bd[5]; int bk[5]; int nb = 0, ncand = 0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { bd[q] = INFINITY; bk[q] = 0; }
+    const int ipx = f2i_rz(me.x), ipy = f2i_rz(me.y);
+    uint32_t* cand = d.cand + (size_t)ga * CE;
+    const PixRect* rects = reinterpret_cast<const PixRect*>(d.car_rect) + (size_t)env * CE;
+    for (int k = 0; k < nc; ++k) {
+        float ox, oy, oh;
+        bool k_alive = true;
+        if (k < N) { const int j = env * N + k; ox = d.ex[j]; oy = d.ey[j]; oh = d.eh[j]; k_alive = d.ealive[j] != 0; }
+        else { const int j = env * d.M + (k - N); ox = d.nx[j]; oy = d.ny[j]; oh = d.nh[j]; }
+        // ---- beam candidates.  Lidar.cpp:57-63: the ego itself, and anything within 1e-3 of its pose, is transparent;
+        //      beams reach at most 248 px (+1 px truncation) from the origin pixel
+        const bool same = fabsf(ox - me.x) < 1e-3f && fabsf(oy - me.y) < 1e-3f && fabsf(oh - me.h) < 1e-3f;
+        if (!same && mode == LIDAR_MARCH) {
+            const PixRect r = rects[k];                // written by k_ego / k_traffic earlier in this step
+            if (!(r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250)) {
+                const BeamWindow w = beam_window(r, me.x, me.y, me.h, R);
+                cand[ncand++] = (uint32_t)k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16);
+            }
+        }
+        // ---- five nearest other alive cars, ascending distance, ties by list order (stable, :466-492)
+        if (k == self || !k_alive) continue;
+        const float dx = ox - me.x, dy = oy - me.y;
+        const float dist = fsqrt_rn(dx * dx + dy * dy);
+        int pos = 0;                               // stable insertion slot = number of kept entries <= dist
+#pragma unroll
+        for (int q = 0; q < 5; ++q) pos += (bd[q] <= dist) ? 1 : 0;
+#pragma unroll
+        for (int q = 4; q >= 1; --q) if (q > pos) { bd[q] = bd[q - 1]; bk[q] = bk[q - 1]; }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) if (q == pos) { bd[q] = dist; bk[q] = k; }
+        if (nb < 5) ++nb;
+    }
+    d.cand_n[ga] = ncand;
+    {
+        const F2* path = d.route_path + (size_t)self * PATH_LEN;
+        float f6[6];
+        obs_ego_features(me, path[min(d.epidx[ga] + 10, PATH_LEN - 1)], f6);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) orow[i] = f6[i];
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        if (q >= nb) break;
+        const int k = bk[q];
+        Pose ot; int intent;
+        if (k < N) { const int j = env * N + k; ot = Pose{d.ex[j], d.ey[j], d.ev[j], d.eh[j]}; intent = d.route_meta[k].intent; }
+        else { const int j = env * d.M + (k - N); ot = Pose{d.nx[j], d.ny[j], d.nv[j], d.nh[j]}; intent = d.route_meta[N + d.nroute[j]].intent; }
+        float f5[5];
+        obs_neighbor_features(me, ot, intent, f5);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) orow[6 + 5 * q + i] = f5[i];
+    }
+    for (int i = 6 + 5 * nb; i < 31; ++i) orow[i] = 0.0f;      // unused neighbour slots stay zero (:424)
 }
 
 // ------------------------------------------------------------------------------------------------ k_lidar_obs
-// Dynamic shared memory of k_lidar_obs, carved at run time: G envs per group, CE = N + M car slots per env.
-struct LidSmem {
-    uint32_t* bits;            // [ROAD_ROWS * ROAD_WORDS]
-    float* rel;                // [ISX_MAX_RAYS]
-    PixRect* rect;             // [G * CE]   lidar pixel rectangle of every car (egos then NPCs)
-    int* ncand;                // [LID_AGENTS] per ego: number of cars a beam can possibly hit
-    int* acb;                  // [LID_AGENTS] first car slot of the ego's env
-    int* aself;                // [LID_AGENTS] ego's slot inside its env
-    uint8_t *ccar, *cia, *cspan;   // [LID_AGENTS * CE] candidate car slot, first beam of its window, window span
-    float *cx, *cy, *cv, *ch;  // [G * CE]
-    int* cintent;              // [G * CE]
-    int* ncars;                // [LID_AGENTS]
-    uint8_t* skip;             // [SKIP_DIM * SKIP_DIM]
-    uint8_t* ealive;           // [LID_AGENTS]
-};
-__host__ __device__ inline size_t lid_carve(unsigned char* base, int G, int CE, LidSmem* s) {
-    size_t o = 0;
-    const size_t nc = (size_t)G * CE;
-    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-    const size_t o_bits = take(sizeof(uint32_t) * ROAD_ROWS * ROAD_WORDS);
-    const size_t o_rel = take(sizeof(float) * ISX_MAX_RAYS);
-    const size_t o_rect = take(sizeof(PixRect) * nc);
-    const size_t o_ncand = take(sizeof(int) * LID_AGENTS), o_acb = take(sizeof(int) * LID_AGENTS), o_aself = take(sizeof(int) * LID_AGENTS);
-    const size_t o_ccar = take((size_t)LID_AGENTS * CE), o_cia = take((size_t)LID_AGENTS * CE), o_cspan = take((size_t)LID_AGENTS * CE);
-    const size_t o_cx = take(sizeof(float) * nc), o_cy = take(sizeof(float) * nc), o_cv = take(sizeof(float) * nc), o_ch = take(sizeof(float) * nc);
-    const size_t o_int = take(sizeof(int) * nc);
-    const size_t o_nc = take(sizeof(int) * LID_AGENTS);
-    const size_t o_skip = take(SKIP_DIM * SKIP_DIM);
-    const size_t o_alive = take(LID_AGENTS);
-    if (s) {
-        s->bits = reinterpret_cast<uint32_t*>(base + o_bits); s->rel = reinterpret_cast<float*>(base + o_rel);
-        s->rect = reinterpret_cast<PixRect*>(base + o_rect);
-        s->ncand = reinterpret_cast<int*>(base + o_ncand); s->acb = reinterpret_cast<int*>(base + o_acb); s->aself = reinterpret_cast<int*>(base + o_aself);
-        s->ccar = base + o_ccar; s->cia = base + o_cia; s->cspan = base + o_cspan;
-        s->cx = reinterpret_cast<float*>(base + o_cx); s->cy = reinterpret_cast<float*>(base + o_cy);
-        s->cv = reinterpret_cast<float*>(base + o_cv); s->ch = reinterpret_cast<float*>(base + o_ch);
-        s->cintent = reinterpret_cast<int*>(base + o_int); s->ncars = reinterpret_cast<int*>(base + o_nc);
-        s->skip = base + o_skip; s->ealive = base + o_alive;
-    }
-    return o;
-}
-
-enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
-
 // Road march for the 32 rays of a warp (must be called by all 32 lanes, converged).  Every lane first takes two
 // accelerated steps of its own ray in lock-step (that finishes ~90% of all rays: mean 1.65 steps/ray); the rays
 // still open are then finished ONE AT A TIME by the whole warp, lane j testing sample k+1+j with the exact pixel
@@ -437,157 +495,85 @@ __device__ __forceinline__ int warp_road_event(bool active, const RoadView& rv, 
     return m.ke;
 }
 
+// One THREAD per (ego, beam), beams of all egos laid end to end; persistent CTAs walk 256-beam chunks, so the only
+// block-level synchronisation is the one after the road tables are staged in shared memory (28 KB per CTA: folded
+// bitmap + skip table + beam angles).  Everything per ego comes from k_features through L1/L2.
 template <int RT>   // RT = beam count known at compile time (72, 96) or 0 = run-time d.R
-__global__ void __launch_bounds__(LID_THREADS, 6)
-k_lidar_obs(const Dev d, int mode, int num_groups, int G) {
+__global__ void __launch_bounds__(LID_THREADS, 8)
+k_lidar_obs(const Dev d, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int N = d.N, R = RT ? RT : d.R;
-    const int CE = N + d.M;
-    const int lane = tid & 31;
-    const RoadView rv{nullptr, nullptr, d.box_lo, d.box_hi};
-    LidSmem s;
-    lid_carve(smem_raw, G, CE, &s);
-    for (int i = tid; i < ROAD_ROWS * ROAD_WORDS; i += LID_THREADS) s.bits[i] = d.road_bits[i];
-    for (int i = tid; i < SKIP_DIM * SKIP_DIM; i += LID_THREADS) s.skip[i] = d.road_skip[i];
-    for (int i = tid; i < R; i += LID_THREADS) s.rel[i] = d.rel_angle[i];
-
-    for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
-        const int env0 = grp * G;
-        const int ng = min(G, d.E - env0);           // envs in this group
-        const int na = ng * N;                        // egos in this group
-        __syncthreads();
-        // ---- stage every car of the group's envs: egos then NPCs, with its lidar pixel rectangle
-        for (int t = tid; t < ng * CE; t += LID_THREADS) {
-            const int g = t / CE, k = t - g * CE;
-            const int env = env0 + g;
-            const int nn = d.traffic ? d.ncount[env] : 0;
-            if (k == 0) s.ncars[g] = N + nn;
-            float x, y, v, h; int intent;
-            if (k < N) {
-                const int ai = env * N + k;
-                x = d.ex[ai]; y = d.ey[ai]; v = d.ev[ai]; h = d.eh[ai]; intent = d.route_meta[k].intent;
-                s.ealive[g * N + k] = d.ealive[ai];
-            } else if (k < N + nn) {
-                const int ni = env * d.M + (k - N);
-                x = d.nx[ni]; y = d.ny[ni]; v = d.nv[ni]; h = d.nh[ni]; intent = d.route_meta[N + d.nroute[ni]].intent;
-            } else continue;
-            s.cx[t] = x; s.cy[t] = y; s.cv[t] = v; s.ch[t] = h; s.cintent[t] = intent;
-            s.rect[t] = car_pixel_rect(x, y, h);
-        }
-        __syncthreads();
-        // ---- per ego: candidate set for the beams + the 31 ego/neighbour features (IntersectionEnv.cpp:431-508)
-        if (tid < na) {
-            const int a = tid, g = a / N, self = a - g * N;
-            const int nc = s.ncars[g];
-            const int cb = g * CE;                 // first car slot of this env
-            const Pose me{s.cx[cb + self], s.cy[cb + self], s.cv[cb + self], s.ch[cb + self]};
-            float* orow = d.obs + ((size_t)env0 * N + a) * ISX_OBS_DIM;      // the 31 feature floats go straight to the row
-            int nb = 0;
-            int ncand = 0;
-            s.acb[a] = cb; s.aself[a] = self;
-            if (s.ealive[a]) {
-                const int ipx = f2i_rz(me.x), ipy = f2i_rz(me.y);
-                for (int k = 0; k < nc; ++k) {
-                    // Lidar.cpp:57-63: the ego itself, and anything within 1e-3 of its pose, is transparent
-                    if (fabsf(s.cx[cb + k] - me.x) < 1e-3f && fabsf(s.cy[cb + k] - me.y) < 1e-3f && fabsf(s.ch[cb + k] - me.h) < 1e-3f) continue;
-                    const PixRect r = s.rect[cb + k];
-                    // beams reach at most 248 px (+1 px truncation) from the origin pixel
-                    if (r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250) continue;
-                    const BeamWindow w = beam_window(r, me.x, me.y, me.h, R);
-                    const int q = a * CE + ncand++;
-                    s.ccar[q] = (uint8_t)k; s.cia[q] = (uint8_t)w.ia; s.cspan[q] = (uint8_t)w.span;
-                }
-                const F2* path = d.route_path + (size_t)self * PATH_LEN;
-                const int pidx = d.epidx[(env0 + g) * N + self];
-                float f6[6];
-                obs_ego_features(me, path[min(pidx + 10, PATH_LEN - 1)], f6);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) orow[i] = f6[i];
-                // five nearest other alive cars, ascending distance, ties by list order (stable, :490)
-                float bd[5]; int bk[5];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) { bd[q] = INFINITY; bk[q] = 0; }
-                for (int k = 0; k < nc; ++k) {
-                    if (k == self) continue;
-                    if (k < N && !s.ealive[g * N + k]) continue;
-                    const float dx = s.cx[cb + k] - me.x, dy = s.cy[cb + k] - me.y;
-                    const float dist = fsqrt_rn(dx * dx + dy * dy);
-                    int pos = 0;                       // stable insertion slot = number of kept entries <= dist
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) pos += (bd[q] <= dist) ? 1 : 0;
-#pragma unroll
-                    for (int q = 4; q >= 1; --q) if (q > pos) { bd[q] = bd[q - 1]; bk[q] = bk[q - 1]; }
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) if (q == pos) { bd[q] = dist; bk[q] = k; }
-                    if (nb < 5) ++nb;
-                }
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    if (q >= nb) break;
-                    const int k = bk[q];
-                    const Pose ot{s.cx[cb + k], s.cy[cb + k], s.cv[cb + k], s.ch[cb + k]};
-                    float f5[5];
-                    obs_neighbor_features(me, ot, s.cintent[cb + k], f5);
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) orow[6 + 5 * q + i] = f5[i];
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) orow[i] = 0.0f;
-            }
-            for (int i = 6 + 5 * nb; i < 31; ++i) orow[i] = 0.0f;          // unused neighbour slots stay zero (:424)
-            s.ncand[a] = ncand;
-        }
-        __syncthreads();
-        // ---- beams: one thread per (ego, beam); the trip count is uniform so that warps stay converged for the
-        //      cooperative part of the road march
-        const RoadView road{s.bits, s.skip, rv.box_lo, rv.box_hi};
-        const int items = na * R;
-        for (int t0 = 0; t0 < items; t0 += LID_THREADS) {
-            const int t = t0 + tid;
-            const bool valid = t < items;
-            const int tc = valid ? t : 0;
-            const int a = tc / R, i = tc - a * R;
-            const int cb = s.acb[a], self = s.aself[a];
-            const size_t ga = (size_t)env0 * N + a;
-            const bool alive = valid && s.ealive[a];
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);
+    uint8_t* s_skip = smem_raw + ROAD_BITS_BYTES;
+    float* s_rel = reinterpret_cast<float*>(smem_raw + ROAD_BITS_BYTES + ROAD_SKIP_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int R = RT ? RT : d.R;
+    {   // 16-byte copies; the global tables are padded to ROAD_*_BYTES
+        const uint4* gb = reinterpret_cast<const uint4*>(d.road_bits);
+        const uint4* gs = reinterpret_cast<const uint4*>(d.road_skip);
+        uint4* sb = reinterpret_cast<uint4*>(s_bits);
+        uint4* ss = reinterpret_cast<uint4*>(s_skip);
+        for (int i = tid; i < ROAD_BITS_BYTES / 16; i += LID_THREADS) sb[i] = gb[i];
+        for (int i = tid; i < ROAD_SKIP_BYTES / 16; i += LID_THREADS) ss[i] = gs[i];
+        for (int i = tid; i < R; i += LID_THREADS) s_rel[i] = d.rel_angle[i];
+    }
+    __syncthreads();
+    const RoadView road{s_bits, s_skip, d.box_lo, d.box_hi};
+    const int CE = d.N + d.M;
+    const long long total = (long long)d.E * d.N * R;
+    const AgentRec* recs = reinterpret_cast<const AgentRec*>(d.agent_rec);
+    const PixRect* rects = reinterpret_cast<const PixRect*>(d.car_rect);
+    // Dynamic work distribution at WARP granularity.  A warp's total time is a sum of very uneven 32-beam pieces
+    // (open road vs. wall vs. off screen); with static striding the slowest of ~9,500 warps — a +3.7 sigma outlier —
+    // set the kernel time at 67% average occupancy.  Each warp now claims WARP_GRAB consecutive 32-beam pieces at a
+    // time from one global counter (zeroed by k_features, which always runs just before) until the beams run out.
+    const long long pieces = (total + 31) / 32;
+    while (true) {
+        long long p0 = 0;
+        if (lane == 0) p0 = (long long)atomicAdd(d.ray_counter, (unsigned)WARP_GRAB);
+        p0 = __shfl_sync(FULL, p0, 0);
+        if (p0 >= pieces) break;
+        const long long p1 = (p0 + WARP_GRAB < pieces) ? p0 + WARP_GRAB : pieces;
+        for (long long pc = p0; pc < p1; ++pc) {
+            const long long id = pc * 32 + lane;
+            const bool valid = id < total;
+            const int ga = valid ? (int)(id / R) : 0;
+            const int i = valid ? (int)(id - (long long)ga * R) : 0;
+            const AgentRec rec = recs[ga];
+            const bool alive = valid && rec.rect_base >= 0;
             float out = 0.0f;                                   // dead ego: all-zero row (:426-429)
             if (mode == LIDAR_FROM_HITS) {
                 if (alive) {
-                    const int k = d.lidar_hit[ga * ISX_MAX_RAYS + i];
+                    const int k = d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i];
                     out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
                 }
             } else {
                 Ray ray = make_ray(0.0f, 0.0f, 1.0f, 0.0f);
                 if (alive) {
                     float sn, cs;
-                    sincosf_(s.ch[cb + self] + s.rel[i], &sn, &cs);
-                    ray = make_ray(s.cx[cb + self], s.cy[cb + self], cs, -sn);
+                    sincosf_(rec.h + s_rel[i], &sn, &cs);
+                    ray = make_ray(rec.x, rec.y, cs, -sn);
                 }
                 bool hit;
                 const int ke = warp_road_event(alive, road, ray, &hit, lane);
                 if (alive) {
                     int best = hit ? ke : 0;
                     int lim = ke - 1;                           // cars only count strictly before the road event
-                    const int nc = s.ncand[a];
-                    const int iw = (i == R - 1) ? 0 : i;         // beam R-1 duplicates beam 0
+                    const int nc = d.cand_n[ga];
+                    const uint32_t* cand = d.cand + (size_t)ga * CE;
+                    const int iw = (i == R - 1) ? 0 : i;        // beam R-1 duplicates beam 0
                     for (int j = 0; j < nc && lim >= 1; ++j) {
-                        const int q = a * CE + j;
-                        const int span = s.cspan[q];
-                        if (span < 255) {                        // angular window of this car (beam_window)
-                            int dlt = iw - (int)s.cia[q];
-                            if (dlt < 0) dlt += R - 1;
-                            if (dlt > span) continue;
-                        }
-                        const int kh = ray_rect_first_hit(s.rect[cb + s.ccar[q]], ray, lim);
+                        const uint32_t ci = cand[j];
+                        int dlt = iw - (int)((ci >> 8) & 255u);  // angular window of this car (beam_window); span 255 = all
+                        dlt += (dlt >> 31) & (R - 1);
+                        if (dlt > (int)(ci >> 16)) continue;
+                        const int kh = ray_rect_first_hit(rects[rec.rect_base + (int)(ci & 255u)], ray, lim);
                         if (kh) { best = kh; lim = kh - 1; }
                     }
-                    d.lidar_hit[ga * ISX_MAX_RAYS + i] = (uint8_t)best;
+                    d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i] = (uint8_t)best;
                     out = (best ? (float)(4 * best) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
                 }
             }
-            if (valid) d.obs[ga * ISX_OBS_DIM + 31 + i] = out;
+            if (valid) d.obs[(size_t)ga * ISX_OBS_DIM + 31 + i] = out;
         }
     }
 }
@@ -650,21 +636,42 @@ __global__ void k_math_probe(int n, const float* a, const float* b, float* sn, f
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-size_t lidar_smem_bytes(const Dev& d) { const int G = max(1, LID_AGENTS / d.N); return lid_carve(nullptr, G, d.N + d.M, nullptr); }
+size_t lidar_smem_bytes(const Dev& d) { (void)d; return (size_t)ROAD_BITS_BYTES + ROAD_SKIP_BYTES + sizeof(float) * ISX_MAX_RAYS; }
+size_t road_bits_bytes() { return ROAD_BITS_BYTES; }
+size_t road_skip_bytes() { return ROAD_SKIP_BYTES; }
 
 cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float spawn_prob, cudaStream_t st) {
-    const int blocks = (d.E + DYN_WARPS - 1) / DYN_WARPS;
-    k_dynamics<<<blocks, DYN_WARPS * 32, 0, st>>>(d, actions, dt, spawn_prob);
+    if (d.traffic) {
+        const int blocks = (d.E + DYN_WARPS - 1) / DYN_WARPS;
+        k_traffic<<<blocks, DYN_WARPS * 32, 0, st>>>(d, dt, spawn_prob);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    const int NP = d.N <= 1 ? 1 : d.N <= 2 ? 2 : d.N <= 4 ? 4 : d.N <= 8 ? 8 : d.N <= 16 ? 16 : 32;
+    const long long threads = ((long long)d.E * NP + 31) / 32 * 32;
+    const int blocks = (int)((threads + 127) / 128);
+    switch (NP) {
+        case 1: k_ego<1><<<blocks, 128, 0, st>>>(d, actions, dt); break;
+        case 2: k_ego<2><<<blocks, 128, 0, st>>>(d, actions, dt); break;
+        case 4: k_ego<4><<<blocks, 128, 0, st>>>(d, actions, dt); break;
+        case 8: k_ego<8><<<blocks, 128, 0, st>>>(d, actions, dt); break;
+        case 16: k_ego<16><<<blocks, 128, 0, st>>>(d, actions, dt); break;
+        default: k_ego<32><<<blocks, 128, 0, st>>>(d, actions, dt); break;
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
-    const int G = max(1, LID_AGENTS / d.N);
-    const int groups = (d.E + G - 1) / G;
-    const int grid = min(groups, grid_cap);
+    const int agents = d.E * d.N;
+    k_features<<<(agents + 127) / 128, 128, 0, st>>>(d, mode);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const long long total = (long long)agents * d.R;
+    const long long chunks = (total + LID_THREADS - 1) / LID_THREADS;
+    const int grid = (int)(chunks < grid_cap ? chunks : grid_cap);
     const size_t sm = lidar_smem_bytes(d);
-    if (d.R == 72) k_lidar_obs<72><<<grid, LID_THREADS, sm, st>>>(d, mode, groups, G);
-    else if (d.R == 96) k_lidar_obs<96><<<grid, LID_THREADS, sm, st>>>(d, mode, groups, G);
-    else k_lidar_obs<0><<<grid, LID_THREADS, sm, st>>>(d, mode, groups, G);
+    if (d.R == 72) k_lidar_obs<72><<<grid, LID_THREADS, sm, st>>>(d, mode);
+    else if (d.R == 96) k_lidar_obs<96><<<grid, LID_THREADS, sm, st>>>(d, mode);
+    else k_lidar_obs<0><<<grid, LID_THREADS, sm, st>>>(d, mode);
     return cudaGetLastError();
 }
 cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st) {

@@ -27,9 +27,13 @@
 #if defined(__CUDACC__)
 #define ISX_HD __host__ __device__ __forceinline__
 #define ISX_HDM __host__ __device__ __forceinline__     // member functions
+// Big functions that are called from many places of the dynamics kernel: one out-of-line copy per translation unit,
+// otherwise k_dynamics inlines them into >100 KB of SASS and stalls on instruction fetch (ncu: stall_no_instruction).
+#define ISX_HD_NOINL static __host__ __device__ __noinline__
 #else
 #define ISX_HD static inline
 #define ISX_HDM inline
+#define ISX_HD_NOINL static inline
 #endif
 
 namespace isx {
@@ -351,6 +355,12 @@ ISX_HD float hypotf_(float x, float y) {
     const double dx = (double)x, dy = (double)y;
     return (float)dsqrt_rn(dx * dx + dy * dy);
 }
+
+// Out-of-line entry points (same arithmetic) for callers where code size matters more than call overhead.
+ISX_HD_NOINL void sincosf_nc(float y, float* sinp, float* cosp) { sincosf_(y, sinp, cosp); }
+ISX_HD_NOINL float tanf_nc(float x) { return tanf_(x); }
+ISX_HD_NOINL float atan2f_nc(float y, float x) { return atan2f_(y, x); }
+ISX_HD_NOINL float hypotf_nc(float x, float y) { return hypotf_(x, y); }
 
 // ---------------------------------------------------------------- helpers used all over the sim
 ISX_HD float fmodf_(float a, float b) { return fmodf(a, b); }

@@ -77,7 +77,7 @@ ISX_HD bool is_line_px(int lanes, int x, int y) {
 
 // ---------------------------------------------------------------- car
 // Car::update (Car.cpp:9-40).  Kinematic bicycle; NOTE the pose step has no dt (px per frame).
-ISX_HD void car_update(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt) {
+ISX_HD_NOINL void car_update(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt) {
     acc = throttle * MAX_ACC;
     const float target = steer_in * MAX_STEERING_ANGLE;
     steer = steer + (target - steer) * 0.2f;
@@ -88,14 +88,14 @@ ISX_HD void car_update(Pose& p, float& steer, float& acc, float throttle, float 
     if (v > PHYSICS_MAX_SPEED) v = PHYSICS_MAX_SPEED;
     float h = p.h;
     if (fabsf(v) > 0.1f) {
-        const float yaw = (v / CAR_LENGTH) * tanf_(steer);
+        const float yaw = (v / CAR_LENGTH) * tanf_nc(steer);
         h = h + yaw;
     }
     h = fmodf_(h + PI_F, TWO_PI_F);
     if (h < 0.0f) h = h + TWO_PI_F;
     h = h - PI_F;
     float s, c;
-    sincosf_(h, &s, &c);
+    sincosf_nc(h, &s, &c);
     p.x = p.x + v * c;
     p.y = p.y - v * s;
     p.v = v;
@@ -140,11 +140,11 @@ ISX_HD bool cars_far_apart(float x1, float y1, float x2, float y2) {
     return dx * dx + dy * dy > 4900.0f;
 }
 
-ISX_HD bool cars_collide(float x1, float y1, float h1, float x2, float y2, float h2) {
+ISX_HD_NOINL bool cars_collide(float x1, float y1, float h1, float x2, float y2, float h2) {
     if (cars_far_apart(x1, y1, x2, y2)) return false;
     float s1, c1, s2, c2;
-    sincosf_(h1, &s1, &c1);
-    sincosf_(h2, &s2, &c2);
+    sincosf_nc(h1, &s1, &c1);
+    sincosf_nc(h2, &s2, &c2);
     float ax[4], ay[4], bx[4], by[4];
     car_corners(x1, y1, s1, c1, ax, ay);
     car_corners(x2, y2, s2, c2, bx, by);
@@ -169,14 +169,14 @@ ISX_HD int path_index_update(const F2* path, int idx, float x, float y) {
 
 // ---------------------------------------------------------------- ego status (IntersectionEnv.cpp:166-290)
 // goal = path[159], prev = path[158].  Returns ISX status code of the car on its own (before car-car).
-ISX_HD int ego_self_status(int lanes, float x, float y, float h, F2 goal, F2 prev) {
+ISX_HD_NOINL int ego_self_status(int lanes, float x, float y, float h, F2 goal, F2 prev) {
     const float dxr = goal.x - prev.x, dyr = goal.y - prev.y;
     bool ok;
     if (fabsf(dxr) > fabsf(dyr)) ok = (fabsf(y - goal.y) < 15.0f) && (fabsf(x - goal.x) < 40.0f);
     else                         ok = (fabsf(x - goal.x) < 15.0f) && (fabsf(y - goal.y) < 40.0f);
     if (ok) return 2;  // SUCCESS
     float s, c, cx[4], cy[4];
-    sincosf_(h, &s, &c);
+    sincosf_nc(h, &s, &c);
     car_corners(x, y, s, c, cx, cy);
     const float lo = -100.0f, hi = (float)WIDTH + 100.0f;
 #pragma unroll
@@ -204,7 +204,7 @@ struct RewardCfg { float k_prog, v_min_ms, k_stuck, k_cv, k_co, k_succ, k_sm, al
 
 ISX_HD float reward_base(const RewardCfg& rc, float x, float y, float v, float acc, float steer, F2 goal,
                          float max_progress, float& prev_dist, float& pa0, float& pa1) {
-    const float cur = hypotf_(x - goal.x, y - goal.y);
+    const float cur = hypotf_nc(x - goal.x, y - goal.y);
     float r_prog = 0.0f;
     if (prev_dist > 0.0f) {
         const float progress = prev_dist - cur;
@@ -225,9 +225,9 @@ ISX_HD float reward_base(const RewardCfg& rc, float x, float y, float v, float a
 // Integer pixel rectangle equivalent to the float AABB test of Lidar.cpp:65-78:
 //   float(px) >= c.x - ex  &&  float(px) <= c.x + ex   <=>   ceil(c.x - ex) <= px <= floor(c.x + ex)
 struct PixRect { int x0, x1, y0, y1; };
-ISX_HD PixRect car_pixel_rect(float x, float y, float h) {
+ISX_HD_NOINL PixRect car_pixel_rect(float x, float y, float h) {
     float s, c;
-    sincosf_(h, &s, &c);
+    sincosf_nc(h, &s, &c);
     const float hl = CAR_LENGTH * 0.5f, hw = CAR_WIDTH * 0.5f;
     const float ex = fabsf(c) * hl + fabsf(s) * hw;
     const float ey = fabsf(s) * hl + fabsf(c) * hw;
@@ -248,7 +248,7 @@ ISX_HD void ray_pixel(float cx, float cy, float dx, float dy, int k, int& px, in
 //   bits : (HALF+1) rows x ROAD_WORDS u32, bit (u,v) = on_road(375+-u, 375+-v)  (the map is mirror-symmetric)
 //   skip : (SKIP_DIM x SKIP_DIM) u8 per 4x4 block of (u,v): samples that can be skipped for sure
 constexpr int ROAD_HALF = 375;               // u,v in [0,375]
-constexpr int ROAD_WORDS = 13;               // 376 bits -> 12 words, padded to an odd stride against bank conflicts
+constexpr int ROAD_WORDS = 12;               // 376 bits -> 12 words (18 KB: 8 CTAs of k_lidar_obs fit one SM)
 constexpr int ROAD_ROWS = ROAD_HALF + 1;
 constexpr int SKIP_DIM = 94;                 // ceil(376/4)
 
@@ -412,7 +412,7 @@ ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
 // at relative angle -pi + i*2pi/(R-1); beam R-1 duplicates beam 0.  The window is widened by one beam on each
 // side (0.065..0.088 rad, against ~1e-6 rad of rounding).  span = 255 means "every beam".
 struct BeamWindow { int ia, span; };
-ISX_HD BeamWindow beam_window(const PixRect& r, float cx, float cy, float heading, int R) {
+ISX_HD_NOINL BeamWindow beam_window(const PixRect& r, float cx, float cy, float heading, int R) {
     BeamWindow w;
     w.ia = 0; w.span = 255;
     if (R < 4) return w;
@@ -450,11 +450,11 @@ ISX_HD bool beam_in_window(const BeamWindow& w, int i, int R) {
 // Pairwise, ghost-index-independent part of the yield logic for NPC `me` against NPC `ot`:
 //   bit0 : `ot` can conflict at all (not same-direction < 60 deg :103-104, not a stable side-by-side car :107-159)
 //   bit1 : yield rules 2-4 hold (:167-176); rule 1 (dist_to_crash < 15) depends on the ghost point.
-ISX_HD int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, float me_cos, float me_dc, bool me_before_ot) {
+ISX_HD_NOINL int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, float me_cos, float me_dc, bool me_before_ot) {
     const float ad = fabsf(wrap_angle(me.h - ot.h));
     if (ad < (60.0f * PI_F / 180.0f)) return 0;
     const float dxt = ot.x - me.x, dyt = ot.y - me.y;
-    const float dto = hypotf_(dxt, dyt);
+    const float dto = hypotf_nc(dxt, dyt);
     if (dto > 1e-5f) {
         const float mx = me_cos, my = -me_sin;
         const float adn = fminf(ad, 2.0f * PI_F - ad);
@@ -466,10 +466,10 @@ ISX_HD int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, float me
                 const float fd = 20.0f;
                 const float mfx = me.x + mx * fd, mfy = me.y + my * fd;
                 float so, co;
-                sincosf_(ot.h, &so, &co);
+                sincosf_nc(ot.h, &so, &co);
                 const float ofx = ot.x + co * fd, ofy = ot.y + (-so) * fd;
                 const float fdx = ofx - mfx, fdy = ofy - mfy;
-                const float fmag = hypotf_(fdx, fdy);
+                const float fmag = hypotf_nc(fdx, fdy);
                 if (fmag > 1e-5f) {
                     const float flon = fdx * mx + fdy * my;
                     const float flat = fsqrt_rn(fmaxf(0.0f, fmag * fmag - flon * flon));
@@ -478,7 +478,7 @@ ISX_HD int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, float me
             }
         }
     }
-    const float ot_dc = hypotf_(ot.x - WIDTH * 0.5f, ot.y - HEIGHT * 0.5f);
+    const float ot_dc = hypotf_nc(ot.x - WIDTH * 0.5f, ot.y - HEIGHT * 0.5f);
     bool y = false;
     if (me.v < 1.0f && ot.v > 3.0f && ot_dc < me_dc + 25.0f) y = true;
     else if (ot_dc < me_dc - 5.0f) y = true;
@@ -489,7 +489,7 @@ ISX_HD int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, float me
 // get_front_car_dist_tf contribution of one other NPC (TrafficFlow.cpp:28-44): its distance, or 1e9.
 ISX_HD float npc_front_candidate(const Pose& me, const Pose& ot, float me_sin, float me_cos) {
     const float dx = ot.x - me.x, dy = ot.y - me.y;
-    const float d = hypotf_(dx, dy);
+    const float d = hypotf_nc(dx, dy);
     if (d > 80.0f) return 1e9f;
     const float vx = me_cos, vy = -me_sin;
     const float dot = (dx * vx + dy * vy) / (d + 1e-5f);
@@ -503,7 +503,7 @@ ISX_HD float npc_front_candidate(const Pose& me, const Pose& ot, float me_sin, f
 // Lateral P-control + cruise thresholds + front-car braking (TrafficFlow.cpp:50-75).
 ISX_HD float npc_steer_cmd(const Pose& me, F2 target) {
     const float dx = target.x - me.x, dy = target.y - me.y;
-    const float err = wrap_angle(atan2f_(-dy, dx) - me.h);
+    const float err = wrap_angle(atan2f_nc(-dy, dx) - me.h);
     return fmaxf(-1.0f, fminf(1.0f, err * 3.0f));
 }
 ISX_HD float npc_cruise_throttle(float v, float front_dist) {
@@ -530,7 +530,7 @@ ISX_HD void obs_ego_features(const Pose& p, F2 target, float* o6) {
     o6[3] = p.h / PI_F;
     const float dx = target.x - p.x, dy = target.y - p.y;
     o6[4] = fsqrt_rn(dx * dx + dy * dy) / (float)WIDTH;
-    o6[5] = wrap_angle(atan2f_(-dy, dx) - p.h) / PI_F;
+    o6[5] = wrap_angle(atan2f_nc(-dy, dx) - p.h) / PI_F;
 }
 ISX_HD void obs_neighbor_features(const Pose& me, const Pose& ot, int intent, float* o5) {
     o5[0] = (ot.x - me.x) / (float)WIDTH;
