@@ -225,7 +225,7 @@ def main():
     for i in range(K):
         flush.zero_()                      # evict L2 between timed steps (outside the event pair)
         ev[i][0].record()
-        env.rollout(1)                     # 2 kernel launches: k_dynamics, k_lidar_obs
+        env.rollout(1)                     # 4 kernel launches: k_traffic, k_ego, k_features, k_lidar_obs
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -254,7 +254,7 @@ def main():
             traffic = json.load(open(rp)).get("k_lidar_obs_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_lidar_obs", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_features+k_lidar_obs (obs producer)", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "us_per_launch": lid_s * 1e6,
                 "k_dynamics_us_per_launch": ms_dyn * 1e3 / kr,
                 "note": "path is issue-bound, not HBM-bound (SURVEY.md §8d): see profiles/ for issue-slot utilisation"}
@@ -304,7 +304,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world, E),
-            "clocks": clocks, "gpu_launches": 2 * K,
+            "clocks": clocks, "gpu_launches": 4 * K,   # k_traffic, k_ego, k_features, k_lidar_obs per step
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "stats": stats, "wall_s_timed_region": t_wall,
             "target_1e9_frac": value / 1e9,

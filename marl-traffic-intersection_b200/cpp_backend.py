@@ -39,6 +39,18 @@ class Car:                       # read-only snapshot with the fields bindings.c
             self.alive, self.intention, self.path_index = bool(cs.alive), int(cs.intention), int(cs.path_index)
 
 
+class Lidar:                     # bindings.cpp:85-93 (default-constructed: 72 beams, Lidar.h:11-14)
+    def __init__(self):
+        self.rays, self.fov_deg, self.max_dist, self.step_size = 72, 360.0, 250.0, 4.0
+        self.distances = [self.max_dist] * self.rays
+        step = self.fov_deg / (self.rays - 1)
+        self.rel_angles = [float(np.float32((np.float32(-180.0) + np.float32(i) * np.float32(step)) * np.float32(np.pi) / np.float32(180.0))) for i in range(self.rays)]
+
+    def normalized(self):
+        inv = (1.0 / self.max_dist) if self.max_dist > 0 else 0.0
+        return [d * inv for d in self.distances]
+
+
 class RewardConfig:              # Reward.h:5-14
     def __init__(self):
         (self.k_prog, self.v_min_ms, self.k_stuck, self.k_cv, self.k_co, self.k_succ, self.k_sm, self.alpha) = reward_vector(None)

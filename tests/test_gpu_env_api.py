@@ -1,0 +1,66 @@
+"""The reference's Python surface (env.py / cpp_backend.py) on top of the CUDA stepper: shapes, dtypes, info keys,
+exception types — the drop-in contract of SURVEY.md §8b."""
+import numpy as np
+import pytest
+
+import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def test_multi_agent_surface_and_values():
+    from marl_traffic_intersection_b200 import IntersectionEnv
+    routes = [("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")]
+    env = IntersectionEnv({"num_agents": 3, "use_team_reward": True, "ego_routes": routes})
+    ref = po.OracleEnv(3, routes, use_team=True)
+    obs, info = env.reset()
+    assert obs.shape == (3, 127) and obs.dtype == np.float32 and info == {}
+    assert (obs.view(np.uint32) == ref.obs().view(np.uint32)).all()
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        a = rng.uniform(-1, 1, (3, 2)).astype(np.float32)
+        obs, rew, term, trunc, info = env.step(a)
+        r = ref.step(a)
+        assert obs.shape == (3, 127) and rew.shape == (3,) and rew.dtype == np.float32
+        assert isinstance(term, bool) and isinstance(trunc, bool)
+        assert set(info) == {"step", "rewards", "collisions", "agents_alive", "terminated", "truncated", "done", "status"}
+        assert (obs.view(np.uint32) == r["obs"].view(np.uint32)).all() and (rew.view(np.uint32) == r["reward"].view(np.uint32)).all()
+        assert info["status"] == [po.STATUS_NAMES[s] for s in r["status"]] and info["done"] == list(r["done"])
+        assert info["collisions"] == {i + 1: po.STATUS_NAMES[s] for i, s in enumerate(r["status"])}
+        assert info["step"] == r["step"] and info["agents_alive"] == r["agents_alive"]
+    assert len(env.cars) == 3 and abs(env.cars[0].state.x - ref.egos()[0]["x"]) == 0
+    with pytest.raises(ValueError):
+        env.step(np.zeros(6, np.float32))          # env.py:178
+    env.close()
+
+
+def test_traffic_mode_forces_single_agent_and_scalar_returns():
+    from marl_traffic_intersection_b200 import IntersectionEnv
+    env = IntersectionEnv({"traffic_flow": True, "num_agents": 5, "traffic_density": 2.0, "seed": 3})
+    assert env.num_agents == 1                          # env.py:87-90
+    obs, _ = env.reset()
+    assert obs.shape == (127,)
+    ref = po.OracleEnv(3, [("IN_1", "OUT_4")], traffic=True, density=2.0, seed=3)
+    for _ in range(200):
+        obs, rew, term, trunc, info = env.step([0.3, 0.0])
+        r = ref.step([[0.3, 0.0]])
+        assert obs.shape == (127,) and isinstance(rew, float) and isinstance(info["rewards"], float)
+        assert (obs.view(np.uint32) == r["obs"][0].view(np.uint32)).all()
+        assert len(env.traffic_cars) == len(ref.npcs())
+    env.close()
+
+
+def test_error_behaviour():
+    from marl_traffic_intersection_b200 import BatchedIntersectionEnv, IntersectionEnv, cpp_backend
+    with pytest.raises(IndexError):
+        IntersectionEnv({"num_agents": 1, "ego_routes": [("IN_6", "OUT_99")]})        # RouteGen.cpp:120 -> IndexError
+    e = cpp_backend.IntersectionEnv(3)
+    e.reset()
+    e.add_car_with_route("IN_99", "OUT_2")                                           # silent no-op, IntersectionEnv.cpp:79-82
+    e.add_car_with_route("IN_6", "OUT_2")
+    assert len(e.get_observations()) == 1
+    r = e.step([], [])                                                               # missing actions -> 0, :153-154
+    assert len(r.obs) == 1 and r.agent_ids == [1] and r.step == 1
+    with pytest.raises(ValueError):
+        BatchedIntersectionEnv({"num_envs": 2, "num_agents": 2, "ego_routes": [("IN_6", "OUT_2")]})
+    assert cpp_backend.has_cpp_backend()
