@@ -28,7 +28,8 @@ def test_multi_agent_surface_and_values():
         assert info["status"] == [po.STATUS_NAMES[s] for s in r["status"]] and info["done"] == list(r["done"])
         assert info["collisions"] == {i + 1: po.STATUS_NAMES[s] for i, s in enumerate(r["status"])}
         assert info["step"] == r["step"] and info["agents_alive"] == r["agents_alive"]
-    assert len(env.cars) == 3 and abs(env.cars[0].state.x - ref.egos()[0]["x"]) == 0
+    assert len(env.cars) == 3 and env.cars[0].state.x == 720.0      # reset-time snapshot, as in the reference (env.py:152)
+    assert env.env.cars[0].state.x == float(ref.egos()[0]["x"])   # a fresh by-value copy, like the pybind property
     with pytest.raises(ValueError):
         env.step(np.zeros(6, np.float32))          # env.py:178
     env.close()
