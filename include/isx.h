@@ -147,6 +147,13 @@ int isx_step(isx_handle *h, const float *actions_dev, float dt, void *stream);
 int isx_step_host(isx_handle *h, const float *actions, float dt, float *obs, float *reward, uint8_t *done,
                   uint8_t *status, uint8_t *terminated, uint8_t *truncated, void *stream);
 
+/* Zero-copy variant of isx_step_host: the library owns PINNED host staging buffers (isx_host_views); the caller writes
+ * actions into the `actions` view, calls isx_step_pinned, and reads results from the other views (valid until the next
+ * host-buffer step).  The device->host copies are pipelined behind the kernels shard by shard.  Synchronous. */
+int isx_step_pinned(isx_handle *h, float dt, void *stream);
+int isx_host_views(isx_handle *h, float **actions, float **obs, float **reward, uint8_t **done, uint8_t **status,
+                   uint8_t **terminated, uint8_t **truncated);
+
 /* `steps` consecutive steps with actions drawn on the device from the Philox action stream
  * (DESIGN.md "RNG streams"); with auto_reset this is the random-action rollout BASELINE.json quotes. */
 int isx_rollout(isx_handle *h, int32_t steps, float dt, void *stream);

@@ -150,20 +150,34 @@ class BatchedIntersectionEnv:
                 "lidar_hit": b["lidar_hit"], "npc_count": b["npc_count"], "events": b["events"]}
         return b["obs"], b["reward"], b["terminated"].bool(), b["truncated"].bool(), info
 
-    def step_host(self, actions: np.ndarray, dt: float = 1.0 / 60.0):
-        """The same step through HOST buffers (what env.py's list<->numpy conversions amount to)."""
-        E, N = self.num_envs, self.num_agents
-        a = np.ascontiguousarray(np.asarray(actions, dtype=np.float32).reshape(E, N, 2))
-        obs = np.empty((E, N, _lib.OBS_DIM), np.float32)
-        rew = np.empty((E, N), np.float32)
-        done = np.empty((E, N), np.uint8)
-        status = np.empty((E, N), np.uint8)
-        term = np.empty(E, np.uint8)
-        trunc = np.empty(E, np.uint8)
-        _lib.check(self._lib, self._lib.isx_step_host(self._h, a.ctypes.data, C.c_float(dt), obs.ctypes.data, rew.ctypes.data,
-                                                       done.ctypes.data, status.ctypes.data, term.ctypes.data, trunc.ctypes.data,
-                                                       self._stream()))
-        return obs, rew, done, status, term.astype(bool), trunc.astype(bool)
+    def _host_views(self):
+        if getattr(self, "_hv", None) is None:
+            ptrs = [C.c_void_p() for _ in range(7)]
+            _lib.check(self._lib, self._lib.isx_host_views(self._h, *[C.byref(p) for p in ptrs]))
+            E, N = self.num_envs, self.num_agents
+
+            def view(p, shape, ctype, dtype):
+                n = int(np.prod(shape))
+                return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n,)).view(dtype).reshape(shape)
+
+            self._hv = dict(actions=view(ptrs[0], (E, N, 2), C.c_float, np.float32), obs=view(ptrs[1], (E, N, _lib.OBS_DIM), C.c_float, np.float32),
+                            reward=view(ptrs[2], (E, N), C.c_float, np.float32), done=view(ptrs[3], (E, N), C.c_uint8, np.uint8),
+                            status=view(ptrs[4], (E, N), C.c_uint8, np.uint8), terminated=view(ptrs[5], (E,), C.c_uint8, np.uint8),
+                            truncated=view(ptrs[6], (E,), C.c_uint8, np.uint8))
+        return self._hv
+
+    def step_host(self, actions: np.ndarray, dt: float = 1.0 / 60.0, copy: bool = False):
+        """The same step through HOST buffers (what env.py's list<->numpy conversions amount to): host actions in, host
+        obs / reward / done / status / terminated / truncated out.  The returned arrays are views of the library's pinned
+        staging buffers, overwritten by the next host step (copy=True detaches them).  Device->host copies are pipelined
+        behind the kernels shard by shard (isx_step_pinned)."""
+        hv = self._host_views()
+        np.copyto(hv["actions"], np.asarray(actions, dtype=np.float32).reshape(hv["actions"].shape))
+        _lib.check(self._lib, self._lib.isx_step_pinned(self._h, C.c_float(dt), self._stream()))
+        out = (hv["obs"], hv["reward"], hv["done"], hv["status"], hv["terminated"].astype(bool), hv["truncated"].astype(bool))
+        if copy:
+            out = tuple(np.array(x) for x in out)
+        return out
 
     def rollout(self, steps: int, dt: float = 1.0 / 60.0):
         """`steps` steps with on-device Philox actions (random-action rollout of BASELINE.json)."""
@@ -210,6 +224,7 @@ class BatchedIntersectionEnv:
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self.buf = {}
+            self._hv = None
             self._lib.isx_destroy(self._h)
             self._h = None
 

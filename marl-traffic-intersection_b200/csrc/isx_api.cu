@@ -55,6 +55,9 @@ struct isx_handle {
     float* h_obs = nullptr; float* h_reward = nullptr;
     uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;
     float last_dt = -1.0f, last_prob = 0.0f;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_shard[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copy_done = nullptr;
     std::vector<RouteHost> routes;
 };
 
@@ -187,7 +190,7 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     ALLOC(h->d_actions, EN * 2);
     {
         float4* rec; int4* rc;
-        ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN); ALLOC(d.ray_counter, 4);
+        ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN); ALLOC(d.ray_counter, 8);
         d.agent_rec = rec; d.car_rect = rc;
     }
 #undef ALLOC
@@ -223,6 +226,12 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
         isx_destroy(h);
         return fail(ISX_E_CUDA, "pinned host allocation failed");
     }
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_shard[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) { isx_destroy(h); return fail(ISX_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
+    }
     *out = h;
     const int rc = isx_reset(h, nullptr, nullptr);
     if (rc) { isx_destroy(h); *out = nullptr; return rc; }
@@ -235,6 +244,9 @@ int isx_destroy(isx_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 4; ++i) if (h->ev_shard[i]) cudaEventDestroy(h->ev_shard[i]);
+    if (h->ev_copy_done) cudaEventDestroy(h->ev_copy_done);
     if (h->h_actions) cudaFreeHost(h->h_actions);
     if (h->h_obs) cudaFreeHost(h->h_obs);
     if (h->h_reward) cudaFreeHost(h->h_reward);
@@ -332,25 +344,82 @@ int isx_rollout_timed(isx_handle* h, int32_t steps, float dt, void* stream, floa
     return ISX_OK;
 }
 
+// A view of envs [e0, e0+cnt) of the same buffers: every per-env array is contiguous per env, so a shard is the same
+// struct with advanced pointers; RNG stays keyed by the global env id through env_base.
+static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
+    Dev s = d;
+    const size_t oE = (size_t)e0, oEN = oE * d.N, oEM = oE * d.M, oEC = oE * (size_t)(d.N + d.M);
+    s.E = cnt; s.env_base = d.env_base + e0;
+    s.ex += oEN; s.ey += oEN; s.ev += oEN; s.eh += oEN; s.esteer += oEN; s.eacc += oEN; s.epd += oEN; s.epa0 += oEN; s.epa1 += oEN;
+    s.epidx += oEN; s.ealive += oEN;
+    s.nx += oEM; s.ny += oEM; s.nv += oEM; s.nh += oEM; s.nsteer += oEM; s.npidx += oEM; s.nroute += oEM; s.nuid += oEM;
+    s.ncount += oE; s.next_uid += oE; s.step_count += oE; s.tick += oE;
+    s.agent_rec = static_cast<char*>(d.agent_rec) + oEN * 16; s.car_rect = static_cast<char*>(d.car_rect) + oEC * 16;
+    s.cand += oEN * (size_t)(d.N + d.M); s.cand_n += oEN; s.ray_counter = d.ray_counter + shard_idx;
+    s.obs += oEN * ISX_OBS_DIM; s.reward += oEN; s.done += oEN; s.status += oEN;
+    s.terminated += oE; s.truncated += oE; s.agents_alive += oE; s.lidar_hit += oEN * ISX_MAX_RAYS;
+    s.events += oE; s.env_stats += oE * STAT_SLOTS;
+    return s;
+}
+
+// Host-buffer step with the device->host copy PIPELINED behind the kernels: the env range is cut into shards; the
+// kernels of shard c+1 run while the copy engine drains the obs rows of shard c (obs is 127 floats per agent — the
+// copy, not the simulation, bounds the end-to-end rate).  Results land in the handle's pinned staging buffers
+// (isx_host_views); actions are taken from the pinned `actions` view.  Synchronous on return.
+int isx_step_pinned(isx_handle* h, float dt, void* stream) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const Dev& d = h->d;
+    const size_t EN = (size_t)d.E * d.N;
+    const float prob = spawn_prob_for(h, dt);
+    CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * EN * 2, cudaMemcpyHostToDevice, st));
+    const int shards = d.E >= 4 * 256 ? 4 : 1;
+    const int per = (d.E + shards - 1) / shards;
+    for (int c = 0; c < shards; ++c) {
+        const int e0 = c * per, cnt = (e0 + per <= d.E) ? per : d.E - e0;
+        if (cnt <= 0) break;
+        const Dev sd = shard_of(d, e0, cnt, c);
+        const size_t aoff = (size_t)e0 * d.N, an = (size_t)cnt * d.N;
+        CK(launch_dynamics(sd, h->d_actions + aoff * 2, dt, prob, st));
+        CK(launch_lidar_obs(sd, 0, h->lidar_grid, st));
+        CK(cudaEventRecord(h->ev_shard[c], st));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_shard[c], 0));
+        CK(cudaMemcpyAsync(h->h_obs + aoff * ISX_OBS_DIM, d.obs + aoff * ISX_OBS_DIM, sizeof(float) * an * ISX_OBS_DIM, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(h->h_reward + aoff, d.reward + aoff, sizeof(float) * an, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(h->h_done + aoff, d.done + aoff, an, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(h->h_status + aoff, d.status + aoff, an, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(h->h_term + e0, d.terminated + e0, (size_t)cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(h->h_trunc + e0, d.truncated + e0, (size_t)cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    CK(cudaEventRecord(h->ev_copy_done, h->copy_stream));
+    CK(cudaStreamWaitEvent(st, h->ev_copy_done, 0));        // keep the caller's stream ordered after the copies
+    CK(cudaEventSynchronize(h->ev_copy_done));
+    return ISX_OK;
+}
+
+int isx_host_views(isx_handle* h, float** actions, float** obs, float** reward, uint8_t** done, uint8_t** status,
+                   uint8_t** terminated, uint8_t** truncated) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (actions) *actions = h->h_actions;
+    if (obs) *obs = h->h_obs;
+    if (reward) *reward = h->h_reward;
+    if (done) *done = h->h_done;
+    if (status) *status = h->h_status;
+    if (terminated) *terminated = h->h_term;
+    if (truncated) *truncated = h->h_trunc;
+    return ISX_OK;
+}
+
 int isx_step_host(isx_handle* h, const float* actions, float dt, float* obs, float* reward, uint8_t* done, uint8_t* status,
                   uint8_t* terminated, uint8_t* truncated, void* stream) {
     if (!h) return fail(ISX_E_ARG, "null handle");
     if (!actions) return fail(ISX_E_ARG, "actions is null");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CK(cudaSetDevice(h->device));
     const Dev& d = h->d;
     const size_t EN = (size_t)d.E * d.N, E = (size_t)d.E;
     std::memcpy(h->h_actions, actions, sizeof(float) * EN * 2);
-    CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * EN * 2, cudaMemcpyHostToDevice, st));
-    CK(launch_dynamics(d, h->d_actions, dt, spawn_prob_for(h, dt), st));
-    CK(launch_lidar_obs(d, 0, h->lidar_grid, st));
-    if (obs) CK(cudaMemcpyAsync(h->h_obs, d.obs, sizeof(float) * EN * ISX_OBS_DIM, cudaMemcpyDeviceToHost, st));
-    if (reward) CK(cudaMemcpyAsync(h->h_reward, d.reward, sizeof(float) * EN, cudaMemcpyDeviceToHost, st));
-    if (done) CK(cudaMemcpyAsync(h->h_done, d.done, EN, cudaMemcpyDeviceToHost, st));
-    if (status) CK(cudaMemcpyAsync(h->h_status, d.status, EN, cudaMemcpyDeviceToHost, st));
-    if (terminated) CK(cudaMemcpyAsync(h->h_term, d.terminated, E, cudaMemcpyDeviceToHost, st));
-    if (truncated) CK(cudaMemcpyAsync(h->h_trunc, d.truncated, E, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const int rc = isx_step_pinned(h, dt, stream);
+    if (rc) return rc;
     if (obs) std::memcpy(obs, h->h_obs, sizeof(float) * EN * ISX_OBS_DIM);
     if (reward) std::memcpy(reward, h->h_reward, sizeof(float) * EN);
     if (done) std::memcpy(done, h->h_done, EN);

@@ -135,3 +135,25 @@ def test_state_injection_roundtrip_and_resync():
     outs = [refs[e].step(act[e]) for e in range(2)]
     compare_step(b, refs, outs, "after injection")
     b.close()
+
+
+def test_pipelined_host_step_equals_device_step():
+    """isx_step_pinned cuts the env range into 4 shards and overlaps their device->host copies with the next shard's
+    kernels; results must be identical to the single-launch device step (and therefore to the checker)."""
+    import torch
+    cfg = dict(num_envs=1024, num_agents=3, num_lanes=3, ego_routes=[("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")],
+               use_team_reward=True, traffic_flow=True, traffic_density=2.0, seed=21)
+    a_env, b_env = _benv()(cfg), _benv()(cfg)
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        act = rng.uniform(-1, 1, (1024, 3, 2)).astype(np.float32)
+        obs_d, rew_d, term_d, trunc_d, info = a_env.step(torch.from_numpy(act).cuda())
+        obs_h, rew_h, done_h, status_h, term_h, trunc_h = b_env.step_host(act)
+        torch.cuda.synchronize()
+        assert (obs_d.cpu().numpy().view(np.uint32) == obs_h.view(np.uint32)).all(), t
+        assert (rew_d.cpu().numpy().view(np.uint32) == rew_h.view(np.uint32)).all(), t
+        assert (info["status"].cpu().numpy() == status_h).all() and (info["done"].cpu().numpy() == done_h).all()
+        assert (term_d.cpu().numpy() == term_h).all() and (trunc_d.cpu().numpy() == trunc_h).all()
+    for k in ("npc_x", "npc_count", "ego_x", "lidar_hit", "events"):
+        assert (a_env.buf[k].cpu().numpy() == b_env.buf[k].cpu().numpy()).all(), k
+    a_env.close(); b_env.close()
