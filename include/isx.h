@@ -161,6 +161,8 @@ int isx_rollout(isx_handle *h, int32_t steps, float dt, void *stream);
 /* isx_rollout with a CUDA-event pair around each kernel launch (on `stream`); returns the summed device
  * milliseconds of the dynamics kernel and of the lidar+observation kernel.  Synchronous.  Measurement aid. */
 int isx_rollout_timed(isx_handle *h, int32_t steps, float dt, void *stream, float *ms_dynamics, float *ms_lidar_obs);
+/* same, per kernel: ms4 = {k_traffic, k_ego, k_features, k_lidar_obs} */
+int isx_rollout_timed4(isx_handle *h, int32_t steps, float dt, void *stream, float *ms4);
 
 int isx_get_buffers(isx_handle *h, isx_buffers *out);
 int isx_num_envs(isx_handle *h);

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libisx_b200.so")
+LIB_PATH = os.environ.get("ISX_LIB") or os.path.join(HERE, "csrc", "libisx_b200.so")   # ISX_LIB: tuning builds (tools/)
 
 ISX_ABI_VERSION = 1
 OBS_DIM = 127
@@ -71,7 +71,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "isx_last_error", "isx_abi_version", "isx_create", "isx_destroy", "isx_reset", "isx_step", "isx_step_host",
     "isx_step_pinned", "isx_host_views",
-    "isx_rollout", "isx_rollout_timed", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
+    "isx_rollout", "isx_rollout_timed", "isx_rollout_timed4", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
     "isx_observe", "isx_stats_read", "isx_stats_reset", "isx_stats_device_ptr", "isx_route", "isx_math_probe",
 ]
 
@@ -103,6 +103,7 @@ def load_library(path: str | None = None):
     lib.isx_host_views.argtypes = [vp] + [C.POINTER(vp)] * 7
     lib.isx_rollout.argtypes = [vp, i32, f32, vp]
     lib.isx_rollout_timed.argtypes = [vp, i32, f32, vp, C.POINTER(f32), C.POINTER(f32)]
+    lib.isx_rollout_timed4.argtypes = [vp, i32, f32, vp, C.POINTER(f32)]
     lib.isx_get_buffers.argtypes = [vp, C.POINTER(Buffers)]
     lib.isx_num_envs.argtypes = [vp]
     lib.isx_num_agents.argtypes = [vp]

@@ -189,6 +189,12 @@ class BatchedIntersectionEnv:
         _lib.check(self._lib, self._lib.isx_rollout_timed(self._h, int(steps), C.c_float(dt), self._stream(), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def rollout_timed4(self, steps: int, dt: float = 1.0 / 60.0):
+        """per-kernel CUDA-event timing: (ms k_traffic, ms k_ego, ms k_features, ms k_lidar_obs) summed over `steps`."""
+        ms = (C.c_float * 4)()
+        _lib.check(self._lib, self._lib.isx_rollout_timed4(self._h, int(steps), C.c_float(dt), self._stream(), ms))
+        return tuple(ms)
+
     def observe(self):
         _lib.check(self._lib, self._lib.isx_observe(self._h, self._stream()))
         return self.buf["obs"]

@@ -18,6 +18,10 @@ size_t road_bits_bytes();
 size_t road_skip_bytes();
 cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float spawn_prob, cudaStream_t st);
 cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st);
+cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_t st);
+cudaError_t launch_ego(const Dev& d, const float* actions, float dt, cudaStream_t st);
+cudaError_t launch_features(const Dev& d, int mode, cudaStream_t st);
+cudaError_t launch_rays(const Dev& d, int mode, int grid_cap, cudaStream_t st);
 cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t launch_reduce_stats(const Dev& d, cudaStream_t st);
 cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st);
@@ -84,6 +88,8 @@ static cudaError_t push(const std::vector<T>& v, T* dev, size_t off, size_t n) {
 
 extern "C" {
 
+int isx_rollout_timed4(isx_handle* h, int32_t steps, float dt, void* stream, float* ms4);
+
 const char* isx_last_error(void) { return g_err.c_str(); }
 int isx_abi_version(void) { return ISX_ABI_VERSION; }
 
@@ -111,7 +117,7 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     if (cfg->lidar_rays < 1 || cfg->lidar_rays > ISX_MAX_RAYS) return fail(ISX_E_ARG, "lidar_rays must be in [1,%d]", ISX_MAX_RAYS);
     if (cfg->npc_capacity < 0 || cfg->npc_capacity > ISX_MAX_NPC) return fail(ISX_E_ARG, "npc_capacity must be in [0,%d]", ISX_MAX_NPC);
     if (cfg->num_traffic_routes < 0 || cfg->num_traffic_routes > ISX_MAX_ROUTES) return fail(ISX_E_ARG, "num_traffic_routes must be in [0,%d]", ISX_MAX_ROUTES);
-    if ((long long)cfg->num_envs * cfg->num_agents > (1ll << 27)) return fail(ISX_E_ARG, "num_envs * num_agents too large");
+    if ((long long)cfg->num_envs * cfg->num_agents * ISX_MAX_RAYS >= (1ll << 31)) return fail(ISX_E_ARG, "num_envs * num_agents too large (beam index must fit 31 bits)");
     if (!cfg->ego_start || !cfg->ego_end) return fail(ISX_E_ARG, "ego routes missing");
 
     int ndev = 0;
@@ -316,31 +322,44 @@ int isx_rollout(isx_handle* h, int32_t steps, float dt, void* stream) {
 // Same loop as isx_rollout, with a CUDA-event pair around every kernel on the launching stream; returns the
 // summed device time of each kernel (ms).  Synchronises.  Used by bench.py for the roofline line.
 int isx_rollout_timed(isx_handle* h, int32_t steps, float dt, void* stream, float* ms_dynamics, float* ms_lidar_obs) {
-    if (!h) return fail(ISX_E_ARG, "null handle");
+    float ms[4] = {0, 0, 0, 0};
+    const int rc = isx_rollout_timed4(h, steps, dt, stream, ms);
+    if (ms_dynamics) *ms_dynamics = ms[0] + ms[1];
+    if (ms_lidar_obs) *ms_lidar_obs = ms[2] + ms[3];
+    return rc;
+}
+
+// CUDA-event pair around EVERY kernel launch: ms4 = {k_traffic, k_ego, k_features, k_lidar_obs} summed over the steps.
+int isx_rollout_timed4(isx_handle* h, int32_t steps, float dt, void* stream, float* ms4) {
+    if (!h || !ms4) return fail(ISX_E_ARG, "null argument");
     if (steps < 1 || steps > 4096) return fail(ISX_E_ARG, "steps must be in [1,4096]");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
     const float prob = spawn_prob_for(h, dt);
-    std::vector<cudaEvent_t> ev((size_t)steps * 3);
+    std::vector<cudaEvent_t> ev((size_t)steps * 5);
     for (auto& e : ev) CK(cudaEventCreate(&e));
     for (int s = 0; s < steps; ++s) {
-        CK(cudaEventRecord(ev[(size_t)s * 3 + 0], st));
-        CK(launch_dynamics(h->d, nullptr, dt, prob, st));
-        CK(cudaEventRecord(ev[(size_t)s * 3 + 1], st));
-        CK(launch_lidar_obs(h->d, 0, h->lidar_grid, st));
-        CK(cudaEventRecord(ev[(size_t)s * 3 + 2], st));
+        cudaEvent_t* e = &ev[(size_t)s * 5];
+        CK(cudaEventRecord(e[0], st));
+        CK(launch_traffic(h->d, dt, prob, st));
+        CK(cudaEventRecord(e[1], st));
+        CK(launch_ego(h->d, nullptr, dt, st));
+        CK(cudaEventRecord(e[2], st));
+        CK(launch_features(h->d, 0, st));
+        CK(cudaEventRecord(e[3], st));
+        CK(launch_rays(h->d, 0, h->lidar_grid, st));
+        CK(cudaEventRecord(e[4], st));
     }
     CK(cudaStreamSynchronize(st));
-    double a = 0.0, b = 0.0;
-    for (int s = 0; s < steps; ++s) {
-        float t0 = 0, t1 = 0;
-        CK(cudaEventElapsedTime(&t0, ev[(size_t)s * 3 + 0], ev[(size_t)s * 3 + 1]));
-        CK(cudaEventElapsedTime(&t1, ev[(size_t)s * 3 + 1], ev[(size_t)s * 3 + 2]));
-        a += t0; b += t1;
-    }
+    double acc[4] = {0, 0, 0, 0};
+    for (int s = 0; s < steps; ++s)
+        for (int k = 0; k < 4; ++k) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, ev[(size_t)s * 5 + k], ev[(size_t)s * 5 + k + 1]));
+            acc[k] += t;
+        }
     for (auto& e : ev) cudaEventDestroy(e);
-    if (ms_dynamics) *ms_dynamics = (float)a;
-    if (ms_lidar_obs) *ms_lidar_obs = (float)b;
+    for (int k = 0; k < 4; ++k) ms4[k] = (float)acc[k];
     return ISX_OK;
 }
 

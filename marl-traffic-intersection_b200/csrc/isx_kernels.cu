@@ -22,7 +22,14 @@ namespace isx {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int DYN_WARPS = 4;              // envs per CTA in k_dynamics
 constexpr int LID_THREADS = 256;
-constexpr int WARP_GRAB = 4;              // 32-beam pieces a warp claims per atomic in k_lidar_obs
+#ifndef ISX_WARP_GRAB
+#define ISX_WARP_GRAB 2
+#endif
+#ifndef ISX_LOCKSTEP
+#define ISX_LOCKSTEP 2
+#endif
+constexpr int WARP_GRAB = ISX_WARP_GRAB;   // 32-beam pieces a warp claims per atomic in k_lidar_obs
+constexpr int LOCKSTEP = ISX_LOCKSTEP;     // accelerated march steps every lane takes before the cooperative tail
 constexpr int ROAD_BITS_BYTES = ((ROAD_ROWS * ROAD_WORDS * 4 + 15) / 16) * 16;
 constexpr int ROAD_SKIP_BYTES = ((SKIP_DIM * SKIP_DIM + 15) / 16) * 16;
 
@@ -385,80 +392,113 @@ struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE, 
 
 __global__ void __launch_bounds__(128)
 k_features(const Dev d, int mode) {
-    const int ga = blockIdx.x * blockDim.x + threadIdx.x;
+    // FOUR lanes per ego (a "quad"): sub-lane q handles the cars q, q+4, ... of the env, so the dependent chain per
+    // thread is a quarter as long and there are 4x more warps in flight (thread-per-ego ran at 20% occupancy).
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, q = lane & 3, qshift = lane & ~3;
     const int N = d.N, R = d.R;
-    if (ga == 0) *d.ray_counter = 0u;              // work counter of the k_lidar_obs launch that follows in the stream
-    if (ga >= d.E * N) return;
+    const int agents = d.E * N;
+    if (t == 0) *d.ray_counter = 0u;               // work counter of the k_lidar_obs launch that follows in the stream
+    const bool ok = (t >> 2) < agents;
+    const int ga = ok ? (t >> 2) : agents - 1;     // out-of-range quads still take part in the shuffles
     const int env = ga / N, self = ga - env * N;
     const int CE = N + d.M;
     const int nn = d.traffic ? d.ncount[env] : 0;
     const int nc = N + nn;
     const Pose me{d.ex[ga], d.ey[ga], d.ev[ga], d.eh[ga]};
     const bool alive = d.ealive[ga] != 0;
-    AgentRec rec;
-    rec.x = me.x; rec.y = me.y; rec.h = me.h; rec.rect_base = alive ? env * CE : -1;
-    reinterpret_cast<AgentRec*>(d.agent_rec)[ga] = rec;
-    float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
-    if (!alive) {                                  // dead ego: all-zero row (:426-429)
-        for (int i = 0; i < 31; ++i) orow[i] = 0.0f;
-        d.cand_n[ga] = 0;
-        return;
+    if (ok && q == 0) {
+        AgentRec rec;
+        rec.x = me.x; rec.y = me.y; rec.h = me.h; rec.rect_base = alive ? env * CE : -1;
+        reinterpret_cast<AgentRec*>(d.agent_rec)[ga] = rec;
     }
-    float bd[5]; int bk[5]; int nb = 0, ncand = 0;
+    float bd[5]; int bk[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) { bd[q] = INFINITY; bk[q] = 0; }
+    for (int i = 0; i < 5; ++i) { bd[i] = INFINITY; bk[i] = 0x7fffffff; }
     const int ipx = f2i_rz(me.x), ipy = f2i_rz(me.y);
     uint32_t* cand = d.cand + (size_t)ga * CE;
     const PixRect* rects = reinterpret_cast<const PixRect*>(d.car_rect) + (size_t)env * CE;
-    for (int k = 0; k < nc; ++k) {
-        float ox, oy, oh;
+    int ncand = 0;
+    const int nc_warp = __reduce_max_sync(FULL, nc);   // the ballot below needs every lane of the warp in the loop
+    for (int k0 = 0; k0 < nc_warp; k0 += 4) {
+        const int k = k0 + q;
+        const bool have = k < nc && alive;
+        float ox = 0, oy = 0, oh = 0;
         bool k_alive = true;
-        if (k < N) { const int j = env * N + k; ox = d.ex[j]; oy = d.ey[j]; oh = d.eh[j]; k_alive = d.ealive[j] != 0; }
-        else { const int j = env * d.M + (k - N); ox = d.nx[j]; oy = d.ny[j]; oh = d.nh[j]; }
+        if (have) {
+            if (k < N) { const int j = env * N + k; ox = d.ex[j]; oy = d.ey[j]; oh = d.eh[j]; k_alive = d.ealive[j] != 0; }
+            else { const int j = env * d.M + (k - N); ox = d.nx[j]; oy = d.ny[j]; oh = d.nh[j]; }
+        }
         // ---- beam candidates.  Lidar.cpp:57-63: the ego itself, and anything within 1e-3 of its pose, is transparent;
         //      beams reach at most 248 px (+1 px truncation) from the origin pixel
-        const bool same = fabsf(ox - me.x) < 1e-3f && fabsf(oy - me.y) < 1e-3f && fabsf(oh - me.h) < 1e-3f;
-        if (!same && mode == LIDAR_MARCH) {
-            const PixRect r = rects[k];                // written by k_ego / k_traffic earlier in this step
-            if (!(r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250)) {
-                const BeamWindow w = beam_window(r, me.x, me.y, me.h, R);
-                cand[ncand++] = (uint32_t)k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16);
+        bool is_cand = false;
+        uint32_t packed = 0;
+        if (have && mode == LIDAR_MARCH) {
+            const bool same = fabsf(ox - me.x) < 1e-3f && fabsf(oy - me.y) < 1e-3f && fabsf(oh - me.h) < 1e-3f;
+            if (!same) {
+                const PixRect r = rects[k];        // written by k_ego / k_traffic earlier in this step
+                if (!(r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250)) {
+                    const BeamWindow w = beam_window(r, me.x, me.y, me.h, R);
+                    packed = (uint32_t)k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16);
+                    is_cand = true;
+                }
             }
         }
-        // ---- five nearest other alive cars, ascending distance, ties by list order (stable, :466-492)
-        if (k == self || !k_alive) continue;
-        const float dx = ox - me.x, dy = oy - me.y;
-        const float dist = fsqrt_rn(dx * dx + dy * dy);
-        int pos = 0;                               // stable insertion slot = number of kept entries <= dist
+        const unsigned qb = (__ballot_sync(FULL, is_cand) >> qshift) & 0xFu;      // this quad's votes, in car order
+        if (is_cand) cand[ncand + __popc(qb & ((1u << q) - 1u))] = packed;
+        ncand += __popc(qb);
+        // ---- own part of the five nearest other alive cars (ascending distance, ties by list order; stable, :466-492)
+        if (have && k != self && k_alive) {
+            const float dx = ox - me.x, dy = oy - me.y;
+            const float dist = fsqrt_rn(dx * dx + dy * dy);
+            int pos = 0;                           // cars arrive in increasing k, so equal distances keep list order
 #pragma unroll
-        for (int q = 0; q < 5; ++q) pos += (bd[q] <= dist) ? 1 : 0;
+            for (int i = 0; i < 5; ++i) pos += (bd[i] <= dist) ? 1 : 0;
 #pragma unroll
-        for (int q = 4; q >= 1; --q) if (q > pos) { bd[q] = bd[q - 1]; bk[q] = bk[q - 1]; }
+            for (int i = 4; i >= 1; --i) if (i > pos) { bd[i] = bd[i - 1]; bk[i] = bk[i - 1]; }
 #pragma unroll
-        for (int q = 0; q < 5; ++q) if (q == pos) { bd[q] = dist; bk[q] = k; }
-        if (nb < 5) ++nb;
+            for (int i = 0; i < 5; ++i) if (i == pos) { bd[i] = dist; bk[i] = k; }
+        }
     }
-    d.cand_n[ga] = ncand;
-    {
-        const F2* path = d.route_path + (size_t)self * PATH_LEN;
-        float f6[6];
-        obs_ego_features(me, path[min(d.epidx[ga] + 10, PATH_LEN - 1)], f6);
+    if (ok && q == 0) d.cand_n[ga] = ncand;
+    // ---- merge the four sorted partial lists: five rounds of a quad-wide lexicographic (distance, list index) minimum
+    float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        float md = bd[0]; int mk = bk[0];
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            const float od = __shfl_xor_sync(FULL, md, o, 4);
+            const int okk = __shfl_xor_sync(FULL, mk, o, 4);
+            if (od < md || (od == md && okk < mk)) { md = od; mk = okk; }
+        }
+        if (mk == bk[0] && mk != 0x7fffffff) {     // this lane's head won: pop it
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { bd[i] = bd[i + 1]; bk[i] = bk[i + 1]; }
+            bd[4] = INFINITY; bk[4] = 0x7fffffff;
+        }
+        // neighbour slot r is written by sub-lane r & 3 (unused slots stay zero, :424)
+        if (ok && (r & 3) == q) {
+            float f5[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (mk != 0x7fffffff) {
+                Pose ot; int intent;
+                if (mk < N) { const int j = env * N + mk; ot = Pose{d.ex[j], d.ey[j], d.ev[j], d.eh[j]}; intent = d.route_meta[mk].intent; }
+                else { const int j = env * d.M + (mk - N); ot = Pose{d.nx[j], d.ny[j], d.nv[j], d.nh[j]}; intent = d.route_meta[N + d.nroute[j]].intent; }
+                obs_neighbor_features(me, ot, intent, f5);
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) orow[6 + 5 * r + i] = f5[i];
+        }
+    }
+    if (ok && q == 1) {                            // the six ego features (:431-458); zeros for a dead ego (:426-429)
+        float f6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (alive) {
+            const F2* path = d.route_path + (size_t)self * PATH_LEN;
+            obs_ego_features(me, path[min(d.epidx[ga] + 10, PATH_LEN - 1)], f6);
+        }
 #pragma unroll
         for (int i = 0; i < 6; ++i) orow[i] = f6[i];
     }
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        if (q >= nb) break;
-        const int k = bk[q];
-        Pose ot; int intent;
-        if (k < N) { const int j = env * N + k; ot = Pose{d.ex[j], d.ey[j], d.ev[j], d.eh[j]}; intent = d.route_meta[k].intent; }
-        else { const int j = env * d.M + (k - N); ot = Pose{d.nx[j], d.ny[j], d.nv[j], d.nh[j]}; intent = d.route_meta[N + d.nroute[j]].intent; }
-        float f5[5];
-        obs_neighbor_features(me, ot, intent, f5);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) orow[6 + 5 * q + i] = f5[i];
-    }
-    for (int i = 6 + 5 * nb; i < 31; ++i) orow[i] = 0.0f;      // unused neighbour slots stay zero (:424)
 }
 
 // ------------------------------------------------------------------------------------------------ k_lidar_obs
@@ -471,7 +511,7 @@ __device__ __forceinline__ int warp_road_event(bool active, const RoadView& rv, 
     m.k = 0; m.px = 0; m.py = 0; m.ke = LIDAR_MAX_K + 1; m.done = true; m.hit = false;
     if (active) march_init(r, m);
 #pragma unroll
-    for (int it = 0; it < 2; ++it)
+    for (int it = 0; it < LOCKSTEP; ++it)
         if (!m.done) march_step(rv, r, m);
     unsigned pend = __ballot_sync(FULL, !m.done);
     while (pend) {
@@ -519,25 +559,25 @@ k_lidar_obs(const Dev d, int mode) {
     __syncthreads();
     const RoadView road{s_bits, s_skip, d.box_lo, d.box_hi};
     const int CE = d.N + d.M;
-    const long long total = (long long)d.E * d.N * R;
+    const int total = d.E * d.N * R;                 // < 2^31, checked by isx_create
     const AgentRec* recs = reinterpret_cast<const AgentRec*>(d.agent_rec);
     const PixRect* rects = reinterpret_cast<const PixRect*>(d.car_rect);
     // Dynamic work distribution at WARP granularity.  A warp's total time is a sum of very uneven 32-beam pieces
     // (open road vs. wall vs. off screen); with static striding the slowest of ~9,500 warps — a +3.7 sigma outlier —
     // set the kernel time at 67% average occupancy.  Each warp now claims WARP_GRAB consecutive 32-beam pieces at a
     // time from one global counter (zeroed by k_features, which always runs just before) until the beams run out.
-    const long long pieces = (total + 31) / 32;
+    const int pieces = (total + 31) / 32;
     while (true) {
-        long long p0 = 0;
-        if (lane == 0) p0 = (long long)atomicAdd(d.ray_counter, (unsigned)WARP_GRAB);
+        int p0 = 0;
+        if (lane == 0) p0 = (int)atomicAdd(d.ray_counter, (unsigned)WARP_GRAB);
         p0 = __shfl_sync(FULL, p0, 0);
         if (p0 >= pieces) break;
-        const long long p1 = (p0 + WARP_GRAB < pieces) ? p0 + WARP_GRAB : pieces;
-        for (long long pc = p0; pc < p1; ++pc) {
-            const long long id = pc * 32 + lane;
+        const int p1 = min(p0 + WARP_GRAB, pieces);
+        for (int pc = p0; pc < p1; ++pc) {
+            const int id = pc * 32 + lane;
             const bool valid = id < total;
-            const int ga = valid ? (int)(id / R) : 0;
-            const int i = valid ? (int)(id - (long long)ga * R) : 0;
+            const int ga = valid ? id / R : 0;
+            const int i = valid ? id - ga * R : 0;
             const AgentRec rec = recs[ga];
             const bool alive = valid && rec.rect_base >= 0;
             float out = 0.0f;                                   // dead ego: all-zero row (:426-429)
@@ -640,13 +680,13 @@ size_t lidar_smem_bytes(const Dev& d) { (void)d; return (size_t)ROAD_BITS_BYTES 
 size_t road_bits_bytes() { return ROAD_BITS_BYTES; }
 size_t road_skip_bytes() { return ROAD_SKIP_BYTES; }
 
-cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float spawn_prob, cudaStream_t st) {
-    if (d.traffic) {
-        const int blocks = (d.E + DYN_WARPS - 1) / DYN_WARPS;
-        k_traffic<<<blocks, DYN_WARPS * 32, 0, st>>>(d, dt, spawn_prob);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
+cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_t st) {
+    if (!d.traffic) return cudaSuccess;
+    const int blocks = (d.E + DYN_WARPS - 1) / DYN_WARPS;
+    k_traffic<<<blocks, DYN_WARPS * 32, 0, st>>>(d, dt, spawn_prob);
+    return cudaGetLastError();
+}
+cudaError_t launch_ego(const Dev& d, const float* actions, float dt, cudaStream_t st) {
     const int NP = d.N <= 1 ? 1 : d.N <= 2 ? 2 : d.N <= 4 ? 4 : d.N <= 8 ? 8 : d.N <= 16 ? 16 : 32;
     const long long threads = ((long long)d.E * NP + 31) / 32 * 32;
     const int blocks = (int)((threads + 127) / 128);
@@ -660,12 +700,18 @@ cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float 
     }
     return cudaGetLastError();
 }
-cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
-    const int agents = d.E * d.N;
-    k_features<<<(agents + 127) / 128, 128, 0, st>>>(d, mode);
-    cudaError_t e = cudaGetLastError();
+cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float spawn_prob, cudaStream_t st) {
+    cudaError_t e = launch_traffic(d, dt, spawn_prob, st);
     if (e != cudaSuccess) return e;
-    const long long total = (long long)agents * d.R;
+    return launch_ego(d, actions, dt, st);
+}
+cudaError_t launch_features(const Dev& d, int mode, cudaStream_t st) {
+    const int agents = d.E * d.N;
+    k_features<<<(agents * 4 + 127) / 128, 128, 0, st>>>(d, mode);
+    return cudaGetLastError();
+}
+cudaError_t launch_rays(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
+    const long long total = (long long)d.E * d.N * d.R;
     const long long chunks = (total + LID_THREADS - 1) / LID_THREADS;
     const int grid = (int)(chunks < grid_cap ? chunks : grid_cap);
     const size_t sm = lidar_smem_bytes(d);
@@ -673,6 +719,11 @@ cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t 
     else if (d.R == 96) k_lidar_obs<96><<<grid, LID_THREADS, sm, st>>>(d, mode);
     else k_lidar_obs<0><<<grid, LID_THREADS, sm, st>>>(d, mode);
     return cudaGetLastError();
+}
+cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
+    cudaError_t e = launch_features(d, mode, st);
+    if (e != cudaSuccess) return e;
+    return launch_rays(d, mode, grid_cap, st);
 }
 cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st) {
     const int n = d.E * d.N;

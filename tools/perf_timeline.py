@@ -16,18 +16,23 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 env = BatchedIntersectionEnv({"num_envs": E, "num_agents": N_AGENTS, "num_lanes": 3, "ego_routes": ROUTES8, "traffic_flow": True,
                               "traffic_density": 1.0, "lidar_rays": 72, "max_steps": 2000, "auto_reset": True, "seed": 0})
+WARM = int(os.environ.get('WARM', '0'))
 env.rollout(3)
 torch.cuda.synchronize()
 env.reset()
-tot_d = tot_l = 0.0
+if WARM:
+    env.rollout(WARM)
+    torch.cuda.synchronize()
+tot = [0.0] * 4
 for b in range(B):
-    d, l = env.rollout_timed(S)
-    tot_d += d
-    tot_l += l
+    ms = env.rollout_timed4(S)
+    tot = [a + x for a, x in zip(tot, ms)]
     npc = env.buf["npc_count"].float().mean().item()
-    print(f"steps {b * S:5d}-{(b + 1) * S:5d}: k_dynamics {1e3 * d / S:7.1f} us  k_lidar_obs {1e3 * l / S:7.1f} us  "
-          f"sum {1e3 * (d + l) / S:7.1f} us  -> {E * N_AGENTS / ((d + l) / S * 1e-3):.3e} agent-steps/s   mean NPCs {npc:.2f}")
+    us = [1e3 * x / S for x in ms]
+    print(f"steps {b * S:5d}-{(b + 1) * S:5d}: traffic {us[0]:6.1f}  ego {us[1]:6.1f}  features {us[2]:6.1f}  rays {us[3]:6.1f}  "
+          f"sum {sum(us):7.1f} us  -> {E * N_AGENTS / (sum(us) * 1e-6):.3e} agent-steps/s   mean NPCs {npc:.2f}")
 n = B * S
-print(f"episode mean: k_dynamics {1e3 * tot_d / n:.1f} us  k_lidar_obs {1e3 * tot_l / n:.1f} us  -> "
-      f"{E * N_AGENTS / ((tot_d + tot_l) / n * 1e-3):.3e} agent-steps/s")
+us = [1e3 * x / n for x in tot]
+print(f"episode mean: traffic {us[0]:.1f}  ego {us[1]:.1f}  features {us[2]:.1f}  rays {us[3]:.1f} us  -> "
+      f"{E * N_AGENTS / (sum(us) * 1e-6):.3e} agent-steps/s")
 print(env.stats())
