@@ -20,7 +20,18 @@
 namespace isx {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int DYN_WARPS = 4;              // envs per CTA in k_dynamics
+#ifndef ISX_DYN_WARPS
+#define ISX_DYN_WARPS 4
+#endif
+#ifndef ISX_EGO_THREADS
+#define ISX_EGO_THREADS 128
+#endif
+#ifndef ISX_FEAT_THREADS
+#define ISX_FEAT_THREADS 128
+#endif
+constexpr int DYN_WARPS = ISX_DYN_WARPS;   // envs (warps) per CTA in k_traffic
+constexpr int EGO_THREADS = ISX_EGO_THREADS;
+constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
 constexpr int LID_THREADS = 256;
 #ifndef ISX_WARP_GRAB
 #define ISX_WARP_GRAB 2
@@ -127,22 +138,38 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     }
     evt.rng_draws = (int)ts.j;
 
-    // -- NPC controller, sequential in list order: NPC i sees the already-updated state of NPCs < i (:337-344)
+    // -- NPC controller (:337-344).  The reference updates NPCs one after the other, NPC i seeing the already-updated
+    //    NPCs < i.  Everything that depends only on an NPC's OWN pre-update state — first path-index update, steering
+    //    command, steering low-pass and its tangent, heading sin/cos, distance to the centre — is evaluated for all NPCs
+    //    at once (lane = NPC); only the parts that look at the other NPCs run in list order.  That cuts the serial
+    //    chain per NPC to about a quarter (the kernel time is the critical path of the env with the most NPCs).
+    Pose cur{0, 0, 0, 0};                       // lane i < c: current state of NPC i
+    float my_steer = 0.0f, my_tan = 0.0f, my_sin = 0.0f, my_cos = 1.0f, my_dc = 0.0f;
+    int my_pidx = 0, my_route = 0;
+    if (lane < c) {
+        cur = Pose{sm.x[lane], sm.y[lane], sm.v[lane], sm.h[lane]};
+        my_route = sm.route[lane];
+        const F2* path = d.route_path + (size_t)(N + my_route) * PATH_LEN;
+        my_pidx = path_index_update(path, sm.pidx[lane], cur.x, cur.y);
+        const float steer_cmd = npc_steer_cmd(cur, path[min(my_pidx + 12, PATH_LEN - 1)]);
+        my_steer = car_steer_update(sm.steer[lane], steer_cmd);
+        my_tan = tanf_nc(my_steer);
+        sincosf_nc(cur.h, &my_sin, &my_cos);
+        my_dc = hypotf_nc(cur.x - WIDTH * 0.5f, cur.y - HEIGHT * 0.5f);
+    }
     for (int i = 0; i < c; ++i) {
-        Pose me{sm.x[i], sm.y[i], sm.v[i], sm.h[i]};
-        float msteer = sm.steer[i], macc = 0.0f;
-        const F2* path = d.route_path + (size_t)(N + sm.route[i]) * PATH_LEN;
-        int mp = warp_path_index(path, sm.pidx[i], me.x, me.y, lane);
-        const float steer_cmd = npc_steer_cmd(me, path[min(mp + 12, PATH_LEN - 1)]);
-        float ms, mc;
-        sincosf_nc(me.h, &ms, &mc);
-        const float me_dc = hypotf_nc(me.x - WIDTH * 0.5f, me.y - HEIGHT * 0.5f);
+        Pose me;
+        me.x = __shfl_sync(FULL, cur.x, i); me.y = __shfl_sync(FULL, cur.y, i);
+        me.v = __shfl_sync(FULL, cur.v, i); me.h = __shfl_sync(FULL, cur.h, i);
+        const float ms = __shfl_sync(FULL, my_sin, i), mc = __shfl_sync(FULL, my_cos, i);
+        const float me_dc = __shfl_sync(FULL, my_dc, i), tan_s = __shfl_sync(FULL, my_tan, i);
+        const int mp0 = __shfl_sync(FULL, my_pidx, i);
+        const F2* path = d.route_path + (size_t)(N + __shfl_sync(FULL, my_route, i)) * PATH_LEN;
         float fc = 1e9f;
         int flags = 0;
         if (lane < c && lane != i) {
-            const Pose ot{sm.x[lane], sm.y[lane], sm.v[lane], sm.h[lane]};
-            fc = npc_front_candidate(me, ot, ms, mc);
-            flags = npc_pair_flags(me, ot, ms, mc, me_dc, i < lane);
+            fc = npc_front_candidate(me, cur, ms, mc);
+            flags = npc_pair_flags(me, cur, ms, mc, me_dc, i < lane);
         }
         const float thr0 = npc_cruise_throttle(me.v, warp_min_f(fc));
         const unsigned elig = __ballot_sync(FULL, flags & 1);
@@ -151,8 +178,8 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         float min_conf = 1e9f;
         if (elig) {                                                // ghost-path scan (:91-185), 32 points per pass
             const float safe_sq = (CAR_WIDTH * 2.0f) * (CAR_WIDTH * 2.0f);
-            const int s1 = min(mp + 120, PATH_LEN);
-            for (int base = mp; base < s1 && !conflict; base += 32) {
+            const int s1 = min(mp0 + 120, PATH_LEN);
+            for (int base = mp0; base < s1 && !conflict; base += 32) {
                 const int g = base + lane;
                 bool hit = false;
                 float dtc = 0.0f;
@@ -174,12 +201,14 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
             }
         }
         const float thr = npc_final_throttle(thr0, conflict, min_conf);
-        car_update(me, msteer, macc, thr, steer_cmd, dt);
-        mp = warp_path_index(path, mp, me.x, me.y, lane);
-        __syncwarp();
-        if (lane == 0) { sm.x[i] = me.x; sm.y[i] = me.y; sm.v[i] = me.v; sm.h[i] = me.h; sm.steer[i] = msteer; sm.pidx[i] = mp; }
+        float macc = 0.0f;
+        car_motion_update(me, macc, thr, tan_s, dt);               // every lane, same operands: uniform
+        const int mp = warp_path_index(path, mp0, me.x, me.y, lane);
+        if (lane == i) { cur = me; my_pidx = mp; sm.x[i] = me.x; sm.y[i] = me.y; }
         __syncwarp();
     }
+    if (lane < c) { sm.v[lane] = cur.v; sm.h[lane] = cur.h; sm.steer[lane] = my_steer; sm.pidx[lane] = my_pidx; }
+    __syncwarp();
 
     // -- NPC-NPC collisions (:347-356): lane j tests the pair (i, j), j > i
     unsigned alive_m = c >= 32 ? FULL : ((1u << c) - 1u);
@@ -236,7 +265,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
 // lanes stay busy (8 egos/env -> 4 envs per warp).  All exchanges between the egos of an env are sub-warp shuffles /
 // ballot slices.  Runs after k_traffic (ego-NPC collisions see the post-update NPCs, :307-317).
 template <int NP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(EGO_THREADS)
 k_ego(const Dev d, const float* __restrict__ actions, float dt) {
     constexpr int EPW = 32 / NP;                                  // envs per warp
     constexpr unsigned LOW = NP == 32 ? 0xffffffffu : ((1u << NP) - 1u);
@@ -390,7 +419,7 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
 enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
 struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE, or -1 for a dead ego
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FEAT_THREADS)
 k_features(const Dev d, int mode) {
     // FOUR lanes per ego (a "quad"): sub-lane q handles the cars q, q+4, ... of the env, so the dependent chain per
     // thread is a quarter as long and there are 4x more warps in flight (thread-per-ego ran at 20% occupancy).
@@ -689,14 +718,14 @@ cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_
 cudaError_t launch_ego(const Dev& d, const float* actions, float dt, cudaStream_t st) {
     const int NP = d.N <= 1 ? 1 : d.N <= 2 ? 2 : d.N <= 4 ? 4 : d.N <= 8 ? 8 : d.N <= 16 ? 16 : 32;
     const long long threads = ((long long)d.E * NP + 31) / 32 * 32;
-    const int blocks = (int)((threads + 127) / 128);
+    const int blocks = (int)((threads + EGO_THREADS - 1) / EGO_THREADS);
     switch (NP) {
-        case 1: k_ego<1><<<blocks, 128, 0, st>>>(d, actions, dt); break;
-        case 2: k_ego<2><<<blocks, 128, 0, st>>>(d, actions, dt); break;
-        case 4: k_ego<4><<<blocks, 128, 0, st>>>(d, actions, dt); break;
-        case 8: k_ego<8><<<blocks, 128, 0, st>>>(d, actions, dt); break;
-        case 16: k_ego<16><<<blocks, 128, 0, st>>>(d, actions, dt); break;
-        default: k_ego<32><<<blocks, 128, 0, st>>>(d, actions, dt); break;
+        case 1: k_ego<1><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
+        case 2: k_ego<2><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
+        case 4: k_ego<4><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
+        case 8: k_ego<8><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
+        case 16: k_ego<16><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
+        default: k_ego<32><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
     }
     return cudaGetLastError();
 }
@@ -707,7 +736,7 @@ cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float 
 }
 cudaError_t launch_features(const Dev& d, int mode, cudaStream_t st) {
     const int agents = d.E * d.N;
-    k_features<<<(agents * 4 + 127) / 128, 128, 0, st>>>(d, mode);
+    k_features<<<(agents * 4 + FEAT_THREADS - 1) / FEAT_THREADS, FEAT_THREADS, 0, st>>>(d, mode);
     return cudaGetLastError();
 }
 cudaError_t launch_rays(const Dev& d, int mode, int grid_cap, cudaStream_t st) {

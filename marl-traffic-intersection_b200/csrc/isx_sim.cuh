@@ -77,10 +77,15 @@ ISX_HD bool is_line_px(int lanes, int x, int y) {
 
 // ---------------------------------------------------------------- car
 // Car::update (Car.cpp:9-40).  Kinematic bicycle; NOTE the pose step has no dt (px per frame).
-ISX_HD_NOINL void car_update(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt) {
-    acc = throttle * MAX_ACC;
+// Split in two so that k_traffic can evaluate the throttle-independent half (steering low-pass + its tangent) for all
+// NPCs in parallel before the sequential planner loop; car_update() below is the plain composition of the halves.
+ISX_HD float car_steer_update(float steer, float steer_in) {                // Car.cpp:14-15
     const float target = steer_in * MAX_STEERING_ANGLE;
-    steer = steer + (target - steer) * 0.2f;
+    return steer + (target - steer) * 0.2f;
+}
+// tan_steer = tanf(new steering angle); only used when |v| > 0.1 (Car.cpp:27-30)
+ISX_HD void car_motion_update(Pose& p, float& acc, float throttle, float tan_steer, float dt) {   // Car.cpp:12,17-39
+    acc = throttle * MAX_ACC;
     float v = p.v;
     if (throttle == 0.0f) v = v * 0.95f;
     v = v + acc * dt;
@@ -88,7 +93,7 @@ ISX_HD_NOINL void car_update(Pose& p, float& steer, float& acc, float throttle, 
     if (v > PHYSICS_MAX_SPEED) v = PHYSICS_MAX_SPEED;
     float h = p.h;
     if (fabsf(v) > 0.1f) {
-        const float yaw = (v / CAR_LENGTH) * tanf_nc(steer);
+        const float yaw = (v / CAR_LENGTH) * tan_steer;
         h = h + yaw;
     }
     h = fmodf_(h + PI_F, TWO_PI_F);
@@ -100,6 +105,10 @@ ISX_HD_NOINL void car_update(Pose& p, float& steer, float& acc, float throttle, 
     p.y = p.y - v * s;
     p.v = v;
     p.h = h;
+}
+ISX_HD_NOINL void car_update(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt) {
+    steer = car_steer_update(steer, steer_in);
+    car_motion_update(p, acc, throttle, tanf_nc(steer), dt);
 }
 
 // Car::corners (Car.cpp:86-103): (+-27, +-12) rotated by +heading (no y flip) — order FL, FR, RR, RL.
@@ -151,14 +160,16 @@ ISX_HD_NOINL bool cars_collide(float x1, float y1, float h1, float x2, float y2,
     return sat_overlap(ax, ay, s1, c1, bx, by, s2, c2);
 }
 
-// Car::update_path_index (Car.cpp:47-74): first minimum of squared distance over path[idx, idx+50).
+// Car::update_path_index (Car.cpp:47-74): first minimum of squared distance over path[idx, min(idx+50,160)).
+// Written as 50 fixed iterations over a clamped index so that the loads are independent of the running minimum and
+// can be issued in batches (the window tail repeats point 159, which can never win a strict `<` against itself).
 ISX_HD int path_index_update(const F2* path, int idx, float x, float y) {
-    int start = idx < 0 ? 0 : idx;
-    int end = start + 50;
-    if (end > PATH_LEN) end = PATH_LEN;
+    const int start = idx < 0 ? 0 : idx;
     float best = INFINITY;
     int bi = start;
-    for (int i = start; i < end; ++i) {
+#pragma unroll 10
+    for (int j = 0; j < 50; ++j) {
+        const int i = (start + j < PATH_LEN) ? start + j : PATH_LEN - 1;
         const F2 p = path[i];
         const float dx = p.x - x, dy = p.y - y;
         const float d = dx * dx + dy * dy;
