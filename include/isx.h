@@ -35,6 +35,7 @@ enum { ISX_OK = 0, ISX_E_ARG = -1, ISX_E_CUDA = -2, ISX_E_ROUTE_START = -3, ISX_
 enum { ISX_ALIVE = 0, ISX_DEAD = 1, ISX_SUCCESS = 2, ISX_CRASH_WALL = 3, ISX_CRASH_LINE = 4, ISX_CRASH_CAR = 5 };
 
 typedef struct isx_handle isx_handle;
+typedef struct isx_snapshot isx_snapshot;
 
 /* Everything env.py passes through IntersectionEnv(num_lanes) / configure / configure_traffic /
  * configure_routes / reward_config.* / add_car_with_route (env.py:111-131,147-152). */
@@ -174,6 +175,16 @@ int isx_get_env_state(isx_handle *h, int32_t env, isx_car_state *egos, isx_car_s
                       int32_t *n_npcs, int32_t *step_count, uint32_t *tick);
 int isx_set_env_state(isx_handle *h, int32_t env, const isx_car_state *egos, const isx_car_state *npcs,
                       int32_t n_npcs, int32_t step_count, uint32_t tick);
+/* Whole-batch device snapshots: get_state()/set_state() of the reference ("fast MCTS rollbacks", EnvState.h:3-15,
+ * IntersectionEnv.cpp:394-416) for all E envs at once, device to device, stream-ordered.  A snapshot holds the full
+ * simulation state (egos, NPCs, counters, RNG tick) AND the last outputs, so the observation after a restore equals
+ * the one at save time; the reference's set_state instead swaps in default 72-beam lidars (:411-415) — that quirk is
+ * deliberately not reproduced.  restore with a mask rolls back only the envs whose byte is non-zero. */
+int isx_snapshot_create(isx_handle *h, isx_snapshot **out);
+int isx_snapshot_save(isx_handle *h, isx_snapshot *s, void *stream);
+int isx_snapshot_restore(isx_handle *h, isx_snapshot *s, const uint8_t *env_mask_dev, void *stream);
+int isx_snapshot_destroy(isx_snapshot *s);
+
 /* get_observations() (IntersectionEnv.cpp:418-520) for the current state, without stepping. */
 int isx_observe(isx_handle *h, void *stream);
 

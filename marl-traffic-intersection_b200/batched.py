@@ -199,6 +199,27 @@ class BatchedIntersectionEnv:
         _lib.check(self._lib, self._lib.isx_observe(self._h, self._stream()))
         return self.buf["obs"]
 
+    # ------------------------------------------------------------------ snapshots (get_state / set_state for the batch)
+    def snapshot(self):
+        """Save the full state of every env on the device (EnvState of the reference, for MCTS-style rollbacks)."""
+        s = C.c_void_p()
+        _lib.check(self._lib, self._lib.isx_snapshot_create(self._h, C.byref(s)))
+        _lib.check(self._lib, self._lib.isx_snapshot_save(self._h, s, self._stream()))
+        self._snaps = getattr(self, "_snaps", [])
+        self._snaps.append(s)
+        return s
+
+    def save_into(self, snap):
+        _lib.check(self._lib, self._lib.isx_snapshot_save(self._h, snap, self._stream()))
+
+    def restore(self, snap, mask: Optional[torch.Tensor] = None):
+        """Roll every env (or those where mask != 0) back to the snapshot."""
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mp = C.c_void_p(mask.data_ptr())
+        _lib.check(self._lib, self._lib.isx_snapshot_restore(self._h, snap, mp, self._stream()))
+
     def stats(self) -> Dict[str, Any]:
         s = _lib.Stats()
         torch.cuda.synchronize(self.device)
@@ -231,6 +252,9 @@ class BatchedIntersectionEnv:
         if getattr(self, "_h", None) is not None and self._h:
             self.buf = {}
             self._hv = None
+            for sn in getattr(self, "_snaps", []):
+                self._lib.isx_snapshot_destroy(sn)
+            self._snaps = []
             self._lib.isx_destroy(self._h)
             self._h = None
 

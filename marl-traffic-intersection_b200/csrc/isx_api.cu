@@ -25,6 +25,7 @@ cudaError_t launch_rays(const Dev& d, int mode, int grid_cap, cudaStream_t st);
 cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t launch_reduce_stats(const Dev& d, cudaStream_t st);
 cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st);
+cudaError_t launch_snapshot_restore(const void* tab, int n_arrays, const uint8_t* mask, int E, cudaStream_t st);
 cudaError_t launch_math_probe(int n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr, cudaStream_t st);
 cudaError_t lidar_set_smem_attr(const Dev& d);
 cudaError_t lidar_occupancy(const Dev& d, int* ctas_per_sm);
@@ -74,6 +75,31 @@ static int dev_alloc(isx_handle* h, T** p, size_t n, bool zero = true) {
     h->allocs.push_back(q);
     *p = static_cast<T*>(q);
     return 0;
+}
+
+// ---- device snapshots (get_state / set_state of the reference, IntersectionEnv.cpp:394-416, for all envs at once)
+struct SnapEntry { unsigned char* live; unsigned char* saved; unsigned bytes_per_env; };
+struct isx_snapshot {
+    isx_handle* owner = nullptr;
+    unsigned char* store = nullptr;       // one allocation holding every saved array
+    void* dev_table = nullptr;            // SnapArray[n] for the masked-restore kernel
+    std::vector<SnapEntry> entries;
+};
+static std::vector<std::pair<void*, unsigned>> snapshot_arrays(const Dev& d) {
+    const unsigned N = (unsigned)d.N, M = (unsigned)d.M;
+    std::vector<std::pair<void*, unsigned>> v;
+    for (float* p : {d.ex, d.ey, d.ev, d.eh, d.esteer, d.eacc, d.epd, d.epa0, d.epa1}) v.push_back({p, 4u * N});
+    v.push_back({d.epidx, 4u * N}); v.push_back({d.ealive, N});
+    for (float* p : {d.nx, d.ny, d.nv, d.nh, d.nsteer}) v.push_back({p, 4u * M});
+    v.push_back({d.npidx, 4u * M}); v.push_back({d.nroute, 4u * M}); v.push_back({d.nuid, 4u * M});
+    v.push_back({d.ncount, 4u}); v.push_back({d.next_uid, 4u}); v.push_back({d.step_count, 4u}); v.push_back({d.tick, 4u});
+    // outputs too, so that the observation after a restore is the observation at save time (the reference instead
+    // resets its lidars to default 72-beam ones in set_state, IntersectionEnv.cpp:411-415 — a quirk not reproduced)
+    v.push_back({d.obs, 4u * N * ISX_OBS_DIM}); v.push_back({d.reward, 4u * N}); v.push_back({d.done, N}); v.push_back({d.status, N});
+    v.push_back({d.terminated, 1u}); v.push_back({d.truncated, 1u}); v.push_back({d.agents_alive, 4u});
+    v.push_back({d.lidar_hit, N * ISX_MAX_RAYS}); v.push_back({d.events, (unsigned)sizeof(isx_traffic_events)});
+    v.push_back({d.car_rect, 16u * (N + M)});
+    return v;
 }
 
 template <class T>
@@ -544,6 +570,59 @@ int isx_set_env_state(isx_handle* h, int32_t env, const isx_car_state* egos, con
     }
     CK(cudaMemcpy(d.step_count + env, &step_count, sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.tick + env, &tick, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return ISX_OK;
+}
+
+int isx_snapshot_create(isx_handle* h, isx_snapshot** out) {
+    if (!h || !out) return fail(ISX_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    isx_snapshot* s = new isx_snapshot();
+    s->owner = h;
+    const auto arrs = snapshot_arrays(h->d);
+    size_t total = 0;
+    for (auto& a : arrs) total += (((size_t)a.second * h->d.E) + 255) & ~(size_t)255;
+    if (cudaMalloc((void**)&s->store, total) != cudaSuccess) { delete s; return fail(ISX_E_CUDA, "snapshot allocation of %zu bytes failed", total); }
+    size_t off = 0;
+    struct Row { unsigned char* live; const unsigned char* saved; unsigned bytes_per_env; };
+    std::vector<Row> rows;
+    for (auto& a : arrs) {
+        s->entries.push_back(SnapEntry{static_cast<unsigned char*>(a.first), s->store + off, a.second});
+        rows.push_back(Row{static_cast<unsigned char*>(a.first), s->store + off, a.second});
+        off += (((size_t)a.second * h->d.E) + 255) & ~(size_t)255;
+    }
+    if (cudaMalloc(&s->dev_table, sizeof(Row) * rows.size()) != cudaSuccess ||
+        cudaMemcpy(s->dev_table, rows.data(), sizeof(Row) * rows.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(s->store); if (s->dev_table) cudaFree(s->dev_table); delete s;
+        return fail(ISX_E_CUDA, "snapshot table upload failed");
+    }
+    *out = s;
+    return ISX_OK;
+}
+int isx_snapshot_destroy(isx_snapshot* s) {
+    if (!s) return ISX_OK;
+    cudaSetDevice(s->owner->device);
+    cudaDeviceSynchronize();
+    cudaFree(s->store);
+    cudaFree(s->dev_table);
+    delete s;
+    return ISX_OK;
+}
+int isx_snapshot_save(isx_handle* h, isx_snapshot* s, void* stream) {
+    if (!h || !s || s->owner != h) return fail(ISX_E_ARG, "snapshot does not belong to this handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    for (auto& e : s->entries) CK(cudaMemcpyAsync(e.saved, e.live, (size_t)e.bytes_per_env * h->d.E, cudaMemcpyDeviceToDevice, st));
+    return ISX_OK;
+}
+int isx_snapshot_restore(isx_handle* h, isx_snapshot* s, const uint8_t* env_mask_dev, void* stream) {
+    if (!h || !s || s->owner != h) return fail(ISX_E_ARG, "snapshot does not belong to this handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    if (!env_mask_dev) {
+        for (auto& e : s->entries) CK(cudaMemcpyAsync(e.live, e.saved, (size_t)e.bytes_per_env * h->d.E, cudaMemcpyDeviceToDevice, st));
+    } else {
+        CK(launch_snapshot_restore(s->dev_table, (int)s->entries.size(), env_mask_dev, h->d.E, st));
+    }
     return ISX_OK;
 }
 

@@ -691,6 +691,24 @@ __global__ void k_reduce_stats(const Dev d) {
     if (threadIdx.x == 15) d.stats[15] = (unsigned long long)__double_as_longlong(racc);
 }
 
+// Masked restore of a snapshot (isx_snapshot_restore): thread per (env, array); copies the env's slice of the array.
+struct SnapArray { unsigned char* live; const unsigned char* saved; unsigned bytes_per_env; };
+__global__ void k_snapshot_restore(const SnapArray* __restrict__ tab, int n_arrays, const uint8_t* __restrict__ mask, int E) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * n_arrays) return;
+    const int env = t / n_arrays, a = t - env * n_arrays;
+    if (mask && !mask[env]) return;
+    const SnapArray s = tab[a];
+    const size_t off = (size_t)env * s.bytes_per_env;
+    unsigned char* dst = s.live + off;
+    const unsigned char* src = s.saved + off;
+    if ((s.bytes_per_env & 3u) == 0 && ((reinterpret_cast<size_t>(dst) | reinterpret_cast<size_t>(src)) & 3u) == 0) {
+        for (unsigned i = 0; i < s.bytes_per_env; i += 4) *reinterpret_cast<uint32_t*>(dst + i) = *reinterpret_cast<const uint32_t*>(src + i);
+    } else {
+        for (unsigned i = 0; i < s.bytes_per_env; ++i) dst[i] = src[i];
+    }
+}
+
 // contraction canary: (a*b + c) with operands chosen so that a fused multiply-add gives a different float
 __global__ void k_canary(float a, float b, float c, float* out) { out[0] = a * b + c; double x = a, y = b, z = c; out[1] = (float)(x * y + z); }
 
@@ -761,6 +779,11 @@ cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st) {
 }
 cudaError_t launch_reduce_stats(const Dev& d, cudaStream_t st) {
     k_reduce_stats<<<1, 1024, 0, st>>>(d);
+    return cudaGetLastError();
+}
+cudaError_t launch_snapshot_restore(const void* tab, int n_arrays, const uint8_t* mask, int E, cudaStream_t st) {
+    const long long n = (long long)E * n_arrays;
+    k_snapshot_restore<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const SnapArray*>(tab), n_arrays, mask, E);
     return cudaGetLastError();
 }
 cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st) {

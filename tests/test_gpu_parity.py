@@ -191,3 +191,35 @@ def test_full_size_shard_invariance_and_spot_check():
     assert s["agent_steps"] == 8192 * 8 * 60 and s["env_resets"] == 8192 and s["npc_overflow"] == 0
     for x in (full, lo, hi):
         x.close()
+
+
+def test_device_snapshot_restore_replays_bit_exactly():
+    """isx_snapshot_save / _restore (the reference's get_state / set_state, for the whole batch, on the device): replaying
+    the same actions from a restored snapshot reproduces every bit; a masked restore rolls back only the chosen envs."""
+    import torch
+    cfg = dict(num_envs=64, num_agents=3, num_lanes=3, ego_routes=[("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")],
+               use_team_reward=True, traffic_flow=True, traffic_density=3.0, seed=31)
+    b = _benv()(cfg)
+    rng = np.random.default_rng(1)
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (64, 3, 2)).astype(np.float32)).cuda() for _ in range(80)]
+    for t in range(40):
+        b.step(acts[t])
+    snap = b.snapshot()
+    obs_at_save = b.buf["obs"].clone()
+    first = []
+    for t in range(40, 80):
+        b.step(acts[t])
+        first.append({k: b.buf[k].clone() for k in ("obs", "reward", "status", "npc_x", "npc_count", "lidar_hit", "ego_x")})
+    b.restore(snap)
+    assert torch.equal(b.buf["obs"], obs_at_save)
+    for i, t in enumerate(range(40, 80)):
+        b.step(acts[t])
+        for k, v in first[i].items():
+            assert torch.equal(b.buf[k], v), (t, k)
+    # masked: roll back the even envs only, then one more common step; odd envs continue from step 80
+    end_state = {k: b.buf[k].clone() for k in ("ego_x", "npc_count", "step")}
+    mask = torch.zeros(64, dtype=torch.uint8, device="cuda"); mask[::2] = 1
+    b.restore(snap, mask)
+    assert torch.equal(b.buf["ego_x"][1::2], end_state["ego_x"][1::2]) and torch.equal(b.buf["step"][1::2], end_state["step"][1::2])
+    assert (b.buf["step"][::2] == 40).all() and torch.equal(b.buf["obs"][::2], obs_at_save[::2])
+    b.close()
