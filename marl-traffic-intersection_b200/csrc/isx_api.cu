@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -220,6 +221,7 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     ALLOC(d.lidar_hit, EN * ISX_MAX_RAYS); ALLOC(d.events, E);
     ALLOC(d.env_stats, E * STAT_SLOTS); ALLOC(d.stats, 16);
     ALLOC(h->d_actions, EN * 2);
+    if (getenv("ISX_TRACE")) ALLOC(d.trace, E * 16); else d.trace = nullptr;
     {
         float4* rec; int4* rc;
         ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN); ALLOC(d.ray_counter, 8);
@@ -637,6 +639,14 @@ int isx_stats_read(isx_handle* h, isx_stats* out) {
     out->npc_collided = (int64_t)raw[ST_COLLIDED]; out->npc_overflow = (int64_t)raw[ST_OVERFLOW];
     out->env_resets = (int64_t)raw[ST_RESETS]; out->agent_steps = (int64_t)raw[ST_STEPS];
     std::memcpy(&out->reward_sum, &raw[15], 8);
+    return ISX_OK;
+}
+int isx_trace_read(isx_handle* h, long long* out16_per_env) {
+    if (!h || !out16_per_env) return fail(ISX_E_ARG, "null argument");
+    if (!h->d.trace) return fail(ISX_E_STATE, "tracing is off (set ISX_TRACE=1 before isx_create)");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out16_per_env, h->d.trace, sizeof(long long) * 16 * (size_t)h->d.E, cudaMemcpyDeviceToHost));
     return ISX_OK;
 }
 int isx_stats_reset(isx_handle* h) {

@@ -61,6 +61,7 @@ struct Dev {
     isx_traffic_events* events;  // [E]
     uint32_t* env_stats;         // [E][STAT_SLOTS]
     unsigned long long* stats;   // [16] reduced counters (slot 15 = reward_sum as double bits)
+    long long* trace;            // optional [E][16] clock64() phase stamps (ISX_TRACE=1 at create; tuning aid), else null
 };
 
 }  // namespace isx

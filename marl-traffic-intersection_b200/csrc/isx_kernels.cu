@@ -71,6 +71,8 @@ __device__ __forceinline__ int warp_path_index(const F2* __restrict__ path, int 
     return bi;
 }
 
+#define ISX_STAMP(slot) do { if (d.trace && lane == 0) d.trace[(size_t)env * 16 + (slot)] = clock64(); } while (0)
+
 struct NpcSmem {
     float x[ISX_MAX_NPC], y[ISX_MAX_NPC], v[ISX_MAX_NPC], h[ISX_MAX_NPC], steer[ISX_MAX_NPC];
     int pidx[ISX_MAX_NPC], route[ISX_MAX_NPC];
@@ -97,6 +99,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     const bool reset_now = d.auto_reset && (d.terminated[env] | d.truncated[env]);   // env.py:147-152 after a done step
     if (reset_now) { c = 0; next_uid = 1; }
     const uint32_t tick = d.tick[env] + 1;
+    ISX_STAMP(0);
 
     isx_traffic_events evt;
     evt.rng_draws = 0; evt.spawn_route = -1; evt.spawned = 0; evt.removed_mask = 0; evt.collided_mask = 0; evt.npc_count = 0;
@@ -137,6 +140,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         }
     }
     evt.rng_draws = (int)ts.j;
+    ISX_STAMP(1);
 
     // -- NPC controller (:337-344).  The reference updates NPCs one after the other, NPC i seeing the already-updated
     //    NPCs < i.  Everything that depends only on an NPC's OWN pre-update state — first path-index update, steering
@@ -157,6 +161,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         sincosf_nc(cur.h, &my_sin, &my_cos);
         my_dc = hypotf_nc(cur.x - WIDTH * 0.5f, cur.y - HEIGHT * 0.5f);
     }
+    ISX_STAMP(2);
     for (int i = 0; i < c; ++i) {
         Pose me;
         me.x = __shfl_sync(FULL, cur.x, i); me.y = __shfl_sync(FULL, cur.y, i);
@@ -171,6 +176,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
             fc = npc_front_candidate(me, cur, ms, mc);
             flags = npc_pair_flags(me, cur, ms, mc, me_dc, i < lane);
         }
+        if (i == 0) ISX_STAMP(8);
         const float thr0 = npc_cruise_throttle(me.v, warp_min_f(fc));
         const unsigned elig = __ballot_sync(FULL, flags & 1);
         const unsigned yld = __ballot_sync(FULL, flags & 2);
@@ -200,16 +206,20 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
                 if (hb) { conflict = true; min_conf = __shfl_sync(FULL, dtc, __ffs(hb) - 1); }
             }
         }
+        if (i == 0) ISX_STAMP(9);
         const float thr = npc_final_throttle(thr0, conflict, min_conf);
         float macc = 0.0f;
         car_motion_update(me, macc, thr, tan_s, dt);               // every lane, same operands: uniform
+        if (i == 0) ISX_STAMP(10);
         const int mp = warp_path_index(path, mp0, me.x, me.y, lane);
+        if (i == 0) ISX_STAMP(11);
         if (lane == i) { cur = me; my_pidx = mp; sm.x[i] = me.x; sm.y[i] = me.y; }
         __syncwarp();
     }
     if (lane < c) { sm.v[lane] = cur.v; sm.h[lane] = cur.h; sm.steer[lane] = my_steer; sm.pidx[lane] = my_pidx; }
     __syncwarp();
 
+    ISX_STAMP(3);
     // -- NPC-NPC collisions (:347-356): lane j tests the pair (i, j), j > i
     unsigned alive_m = c >= 32 ? FULL : ((1u << c) - 1u);
     const unsigned all_m = alive_m;
@@ -222,6 +232,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
             if (m) alive_m &= ~(m | (1u << i));
         }
     }
+    ISX_STAMP(4);
     // -- ordered erase of dead / arrived / out-of-screen (:359-366)
     bool rem = false;
     float mx = 0, my = 0, mv = 0, mh = 0, mst = 0; int mpi = 0, mr = 0; uint32_t mu = 0;
@@ -248,6 +259,8 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     c = __popc(keep_m);
     evt.npc_count = c;
     if (lane == 0) { d.ncount[env] = c; d.next_uid[env] = next_uid; d.events[env] = evt; }
+    ISX_STAMP(5);
+    if (d.trace && lane == 0) d.trace[(size_t)env * 16 + 6] = c;
     {
         uint32_t* st = d.env_stats + (size_t)env * STAT_SLOTS;
         uint32_t inc = 0;

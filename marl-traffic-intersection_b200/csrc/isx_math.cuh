@@ -363,7 +363,19 @@ ISX_HD_NOINL float atan2f_nc(float y, float x) { return atan2f_(y, x); }
 ISX_HD_NOINL float hypotf_nc(float x, float y) { return hypotf_(x, y); }
 
 // ---------------------------------------------------------------- helpers used all over the sim
-ISX_HD float fmodf_(float a, float b) { return fmodf(a, b); }
+// fmodf is exact by definition, so any exact evaluation has libm's bits.  Every call site divides an angle by 2*pi
+// and the quotient is almost always 0 or +-1: |a| < b returns a; b <= |a| < 2b returns a -+ b, which is exact by
+// Sterbenz's lemma (b <= |a| <= 2b).  Anything else takes the generic routine.  (CUDA's generic fmodf is a ~100-cycle
+// dependent chain and sat on the critical path of every small kernel.)
+ISX_HD float fmodf_(float a, float b) {
+    const float aa = fabsf(a), ab = fabsf(b);
+    if (aa < ab) return a;
+    if (aa < 2.0f * ab) {
+        const float r = (a < 0.0f) ? a + ab : a - ab;
+        return (r == 0.0f) ? copysignf(0.0f, a) : r;          // fmod's zero carries the sign of a
+    }
+    return fmodf(a, b);
+}
 
 // wrap to [-pi, pi): IntersectionEnv.cpp:9-13, TrafficFlow.cpp:8-12, Car.cpp:33-36
 ISX_HD float wrap_angle(float a) {

@@ -74,6 +74,14 @@ uint64_t isxm_sweep_sinf_cosf(uint32_t lo, uint32_t hi, int nthreads, uint32_t* 
         return same(s, sinf(vx)) && same(c, cosf(vx));
     });
 }
+// fast exact fmod path vs libm fmodf, as used by wrap_angle (b = 2*pi_f) and with a second modulus
+uint64_t isxm_sweep_fmod(uint32_t lo, uint32_t hi, int nthreads, uint32_t* first_bad) {
+    return sweep(lo, hi, nthreads, first_bad, [](float x) {
+        volatile float vx = x;
+        const float t = isx::TWO_PI_F;
+        return same(isx::fmodf_(x, t), fmodf(vx, t)) && same(isx::fmodf_(x, -t), fmodf(vx, -t)) && same(isx::fmodf_(x, 1.5f), fmodf(vx, 1.5f));
+    });
+}
 uint64_t isxm_sweep_tanf(uint32_t lo, uint32_t hi, int nthreads, uint32_t* first_bad) {
     return sweep(lo, hi, nthreads, first_bad, [](float x) { return same(isx::tanf_(x), tanf(x)); });
 }

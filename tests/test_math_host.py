@@ -14,7 +14,7 @@ NT = os.cpu_count() or 4
 
 def lib():
     l = C.CDLL(LIB)
-    for n in ("isxm_sweep_sincosf", "isxm_sweep_sinf_cosf", "isxm_sweep_tanf", "isxm_sweep_atanf"):
+    for n in ("isxm_sweep_sincosf", "isxm_sweep_sinf_cosf", "isxm_sweep_tanf", "isxm_sweep_atanf", "isxm_sweep_fmod"):
         f = getattr(l, n)
         f.restype = C.c_uint64
         f.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
@@ -25,11 +25,14 @@ def lib():
     return l
 
 
-@pytest.mark.parametrize("fn", ["isxm_sweep_sincosf", "isxm_sweep_sinf_cosf", "isxm_sweep_tanf", "isxm_sweep_atanf"])
+@pytest.mark.parametrize("fn", ["isxm_sweep_sincosf", "isxm_sweep_sinf_cosf", "isxm_sweep_tanf", "isxm_sweep_atanf", "isxm_sweep_fmod"])
 def test_exhaustive_one_argument(fn):
     fb = C.c_uint32()
-    bad = getattr(lib(), fn)(0, 0xFFFFFFFF, NT, C.byref(fb))
-    assert bad == 0, f"{fn}: {bad} mismatches, first at bits {fb.value:#x}"
+    # fmod: all |x| < 2^20 of both signs + inf/nan patterns (libm's generic fmodf is slow on huge quotients)
+    ranges = [(0, 0x49800000), (0x7F000000, 0x7FFFFFFF), (0x80000000, 0xC9800000), (0xFF000000, 0xFFFFFFFF)] if fn == "isxm_sweep_fmod" else [(0, 0xFFFFFFFF)]
+    for lo, hi in ranges:
+        bad = getattr(lib(), fn)(lo, hi, NT, C.byref(fb))
+        assert bad == 0, f"{fn}: {bad} mismatches, first at bits {fb.value:#x}"
 
 
 @pytest.mark.parametrize("other", [1.0, -0.0, -270.0])
