@@ -29,6 +29,15 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef ISX_FEAT_THREADS
 #define ISX_FEAT_THREADS 128
 #endif
+#ifndef ISX_TRAFFIC_MINB
+#define ISX_TRAFFIC_MINB 1
+#endif
+#ifndef ISX_EGO_MINB
+#define ISX_EGO_MINB 1
+#endif
+#ifndef ISX_FEAT_MINB
+#define ISX_FEAT_MINB 1
+#endif
 constexpr int DYN_WARPS = ISX_DYN_WARPS;   // envs (warps) per CTA in k_traffic
 constexpr int EGO_THREADS = ISX_EGO_THREADS;
 constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
@@ -85,7 +94,7 @@ struct NpcSmem {
 // order, NPC-NPC SAT, ordered erase.  The lanes spread over path-window points / other NPCs / ghost-path points.
 // Reads the egos' PRE-step positions (spawn blocking, :244-249), so it runs before k_ego.  Only launched when traffic
 // flow is enabled.
-__global__ void __launch_bounds__(DYN_WARPS * 32)
+__global__ void __launch_bounds__(DYN_WARPS * 32, ISX_TRAFFIC_MINB)
 k_traffic(const Dev d, float dt, float spawn_prob) {
     __shared__ NpcSmem sm_all[DYN_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,7 +287,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
 // lanes stay busy (8 egos/env -> 4 envs per warp).  All exchanges between the egos of an env are sub-warp shuffles /
 // ballot slices.  Runs after k_traffic (ego-NPC collisions see the post-update NPCs, :307-317).
 template <int NP>
-__global__ void __launch_bounds__(EGO_THREADS)
+__global__ void __launch_bounds__(EGO_THREADS, ISX_EGO_MINB)
 k_ego(const Dev d, const float* __restrict__ actions, float dt) {
     constexpr int EPW = 32 / NP;                                  // envs per warp
     constexpr unsigned LOW = NP == 32 ? 0xffffffffu : ((1u << NP) - 1u);
@@ -432,7 +441,7 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
 enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
 struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE, or -1 for a dead ego
 
-__global__ void __launch_bounds__(FEAT_THREADS)
+__global__ void __launch_bounds__(FEAT_THREADS, ISX_FEAT_MINB)
 k_features(const Dev d, int mode) {
     // FOUR lanes per ego (a "quad"): sub-lane q handles the cars q, q+4, ... of the env, so the dependent chain per
     // thread is a quarter as long and there are 4x more warps in flight (thread-per-ego ran at 20% occupancy).
