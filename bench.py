@@ -239,8 +239,9 @@ def main():
 
     # ---------------- per-kernel time for the roofline line (CUDA events around each launch, live)
     kr = min(K, 200)
-    ms_dyn, ms_lid = env.rollout_timed(kr)
-    lid_s = ms_lid * 1e-3 / kr
+    ms4 = env.rollout_timed4(kr)                    # CUDA events around every launch, on the launching stream
+    us4 = [1e3 * x / kr for x in ms4]
+    lid_s = us4[3] * 1e-6                           # dominant kernel: k_lidar_obs
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
@@ -254,10 +255,12 @@ def main():
             traffic = json.load(open(rp)).get("k_lidar_obs_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_features+k_lidar_obs (obs producer)", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "us_per_launch": lid_s * 1e6,
-                "k_dynamics_us_per_launch": ms_dyn * 1e3 / kr,
-                "note": "path is issue-bound, not HBM-bound (SURVEY.md §8d): see profiles/ for issue-slot utilisation"}
+    roofline = {"bound": "hbm", "kernel": "k_lidar_obs", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "us_per_launch": us4[3],
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_AGENT_STEP * E * N_AGENTS,
+                "all_kernels_us_per_launch": {"k_traffic": us4[0], "k_ego": us4[1], "k_features": us4[2], "k_lidar_obs": us4[3]},
+                "note": "the path is instruction-issue-bound, not HBM-bound (SURVEY.md 8d predicted ~1% of the HBM roofline at the "
+                        "target rate): k_lidar_obs issues 0.81 warp-instructions/cycle/SMSP of a possible 1.0 (profiles/r01)"}
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers
     Ke = min(K, 100)

@@ -7,12 +7,7 @@ $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err || { echo "plain run failed"
 tail -1 gpurun_out/plain.log | cut -c1-200
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1610 -c 160 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_lidar_obs -s 405 -c 1 -o gpurun_out/prof_lidar -f $CMD > gpurun_out/ncu_lidar.log 2>&1
-echo "lidar rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_traffic -s 405 -c 1 -o gpurun_out/prof_dyn -f $CMD > gpurun_out/ncu_dyn.log 2>&1
-echo "dyn rc=$?"
-ls -la gpurun_out | head -20
-ncu --set full --clock-control none --import-source on -k regex:k_ego -s 405 -c 1 -o gpurun_out/prof_ego -f $CMD > gpurun_out/ncu_ego.log 2>&1
-echo "ego rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_features -s 405 -c 1 -o gpurun_out/prof_feat -f $CMD > gpurun_out/ncu_feat.log 2>&1
-echo "feat rc=$?"
+for k in k_lidar_obs k_traffic k_ego k_features; do
+ncu --set full --clock-control none --import-source on -k regex:$k -s 405 -c 1 -o gpurun_out/prof_$k -f $CMD > gpurun_out/ncu_$k.log 2>&1
+echo "$k rc=$?"
+done
