@@ -239,6 +239,7 @@ def main():
 
     # ---------------- per-kernel time for the roofline line (CUDA events around each launch, live)
     kr = min(K, 200)
+    env.rollout(300)                                # mid-episode state, so the per-kernel times are representative
     ms4 = env.rollout_timed4(kr)                    # CUDA events around every launch, on the launching stream
     us4 = [1e3 * x / kr for x in ms4]
     lid_s = us4[3] * 1e-6                           # dominant kernel: k_lidar_obs
