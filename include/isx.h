@@ -122,6 +122,7 @@ typedef struct isx_stats {
     int64_t npc_overflow;        /* spawns dropped because the env's NPC slots were full */
     int64_t env_resets;          /* auto-resets performed */
     double reward_sum;
+    int64_t neighbor_tie_sorts;  /* observations whose neighbour order needed the exact std::sort replay (equal distances, > 16 neighbours) */
 } isx_stats;
 
 const char *isx_last_error(void);

@@ -65,7 +65,7 @@ class Buffers(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("agent_steps", C.c_int64), ("status_hist", C.c_int64 * 6), ("npc_spawned", C.c_int64),
                 ("npc_removed", C.c_int64), ("npc_collided", C.c_int64), ("npc_overflow", C.c_int64),
-                ("env_resets", C.c_int64), ("reward_sum", C.c_double)]
+                ("env_resets", C.c_int64), ("reward_sum", C.c_double), ("neighbor_tie_sorts", C.c_int64)]
 
 
 EXPORTS = [

@@ -226,7 +226,8 @@ class BatchedIntersectionEnv:
         _lib.check(self._lib, self._lib.isx_stats_read(self._h, C.byref(s)))
         return {"agent_steps": s.agent_steps, "status_hist": {STATUS_NAMES[i]: s.status_hist[i] for i in range(6)},
                 "npc_spawned": s.npc_spawned, "npc_removed": s.npc_removed, "npc_collided": s.npc_collided,
-                "npc_overflow": s.npc_overflow, "env_resets": s.env_resets, "reward_sum": s.reward_sum}
+                "npc_overflow": s.npc_overflow, "env_resets": s.env_resets, "reward_sum": s.reward_sum,
+                "neighbor_tie_sorts": s.neighbor_tie_sorts}
 
     def stats_tensor(self) -> torch.Tensor:
         """int64[16] device view of the reduced counters (slot 15 = reward_sum bits) for an NCCL all-reduce."""

@@ -639,6 +639,7 @@ int isx_stats_read(isx_handle* h, isx_stats* out) {
     out->npc_collided = (int64_t)raw[ST_COLLIDED]; out->npc_overflow = (int64_t)raw[ST_OVERFLOW];
     out->env_resets = (int64_t)raw[ST_RESETS]; out->agent_steps = (int64_t)raw[ST_STEPS];
     std::memcpy(&out->reward_sum, &raw[15], 8);
+    out->neighbor_tie_sorts = (int64_t)raw[ST_TIESORT];
     return ISX_OK;
 }
 int isx_trace_read(isx_handle* h, long long* out16_per_env) {

@@ -15,7 +15,7 @@ struct RouteMeta {
 };
 
 constexpr int STAT_SLOTS = 16;   // per-env u32 counters; slot 14/15 hold reward_sum (double)
-enum { ST_HIST0 = 0, ST_SPAWNED = 6, ST_REMOVED = 7, ST_COLLIDED = 8, ST_OVERFLOW = 9, ST_RESETS = 10, ST_STEPS = 11, ST_RSUM = 14 };
+enum { ST_HIST0 = 0, ST_SPAWNED = 6, ST_REMOVED = 7, ST_COLLIDED = 8, ST_OVERFLOW = 9, ST_RESETS = 10, ST_STEPS = 11, ST_TIESORT = 12, ST_RSUM = 14 };
 
 struct Dev {
     // ---- configuration

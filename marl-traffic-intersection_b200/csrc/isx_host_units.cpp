@@ -111,6 +111,15 @@ void isxh_traffic_words(uint64_t seed, uint32_t env, uint32_t tick, int n, uint3
     TrafficStream s; s.init(seed, env, tick);
     for (int i = 0; i < n; ++i) out[i] = s.next();
 }
+// neighbour ordering (isx_sim.cuh stdsort): perm_out[i] = list position ranked i; returns the heap-fallback count
+int isxh_std_sort(const float* keys, int n, int32_t* perm_out) {
+    if (n > 255) return -1;
+    uint8_t p[256];
+    for (int i = 0; i < n; ++i) p[i] = (uint8_t)i;
+    const int heaps = stdsort::sort(keys, p, n);
+    for (int i = 0; i < n; ++i) perm_out[i] = p[i];
+    return heaps;
+}
 float isxh_u01_of(uint64_t seed, uint32_t env, uint32_t tick) { TrafficStream s; s.init(seed, env, tick); return s.uniform01(); }
 
 }  // extern "C"

@@ -441,6 +441,34 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
 enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
 struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE, or -1 for a dead ego
 
+// Rare path of k_features: the reference's neighbour list of one ego (other alive egos in index order, then the NPCs in
+// list order, :466-488), ordered by the restated libstdc++ std::sort; returns the car index (ego j, or N + NPC j; 0xff = none) of ranks 0..4,
+// one byte each (by value, so the caller's rank registers never need an address).
+// (plain pointers, not `const Dev&`: taking the address of the kernel parameter would copy it to local memory for everyone)
+__device__ __noinline__ unsigned long long exact_neighbor_top5(const float* __restrict__ ex, const float* __restrict__ ey, const uint8_t* __restrict__ ealive,
+                                                 const float* __restrict__ nx, const float* __restrict__ ny, int N, int M,
+                                                 int env, int self, float mx, float my, int nn) {
+    float key[ISX_MAX_AGENTS + ISX_MAX_NPC];
+    uint8_t src[ISX_MAX_AGENTS + ISX_MAX_NPC], p[ISX_MAX_AGENTS + ISX_MAX_NPC];
+    int m = 0;
+    for (int j = 0; j < N; ++j) {
+        const int g = env * N + j;
+        if (j == self || !ealive[g]) continue;
+        const float dx = ex[g] - mx, dy = ey[g] - my;
+        key[m] = fsqrt_rn(dx * dx + dy * dy); src[m] = (uint8_t)j; p[m] = (uint8_t)m; ++m;
+    }
+    for (int j = 0; j < nn; ++j) {
+        const int g = env * M + j;
+        const float dx = nx[g] - mx, dy = ny[g] - my;
+        key[m] = fsqrt_rn(dx * dx + dy * dy); src[m] = (uint8_t)(N + j); p[m] = (uint8_t)m; ++m;
+    }
+    stdsort::sort(key, p, m);
+    unsigned long long packed = 0;
+    for (int i = 0; i < 5; ++i) packed |= (unsigned long long)(i < m ? src[p[i]] : 0xffu) << (8 * i);
+    return packed;
+}
+
+
 __global__ void __launch_bounds__(FEAT_THREADS, ISX_FEAT_MINB)
 k_features(const Dev d, int mode) {
     // FOUR lanes per ego (a "quad"): sub-lane q handles the cars q, q+4, ... of the env, so the dependent chain per
@@ -464,6 +492,7 @@ k_features(const Dev d, int mode) {
         reinterpret_cast<AgentRec*>(d.agent_rec)[ga] = rec;
     }
     float bd[5]; int bk[5];
+    int nbr = 0;                                   // neighbours this sub-lane saw (the quad total is the list length of :490)
 #pragma unroll
     for (int i = 0; i < 5; ++i) { bd[i] = INFINITY; bk[i] = 0x7fffffff; }
     const int ipx = f2i_rz(me.x), ipy = f2i_rz(me.y);
@@ -502,6 +531,7 @@ k_features(const Dev d, int mode) {
         if (have && k != self && k_alive) {
             const float dx = ox - me.x, dy = oy - me.y;
             const float dist = fsqrt_rn(dx * dx + dy * dy);
+            ++nbr;
             int pos = 0;                           // cars arrive in increasing k, so equal distances keep list order
 #pragma unroll
             for (int i = 0; i < 5; ++i) pos += (bd[i] <= dist) ? 1 : 0;
@@ -512,10 +542,12 @@ k_features(const Dev d, int mode) {
         }
     }
     if (ok && q == 0) d.cand_n[ga] = ncand;
-    // ---- merge the four sorted partial lists: five rounds of a quad-wide lexicographic (distance, list index) minimum
     float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
+    // ---- merge the four sorted partial lists: five rounds of a quad-wide lexicographic (distance, list index) minimum,
+    //      plus a sixth minimum that is only looked at for the tie test below
+    float fd[6]; int fk[5];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
+    for (int r = 0; r < 6; ++r) {
         float md = bd[0]; int mk = bk[0];
 #pragma unroll
         for (int o = 1; o < 4; o <<= 1) {
@@ -523,23 +555,47 @@ k_features(const Dev d, int mode) {
             const int okk = __shfl_xor_sync(FULL, mk, o, 4);
             if (od < md || (od == md && okk < mk)) { md = od; mk = okk; }
         }
-        if (mk == bk[0] && mk != 0x7fffffff) {     // this lane's head won: pop it
+        fd[r] = md;
+        if (r < 5) {
+            fk[r] = mk;
+            if (mk == bk[0] && mk != 0x7fffffff) {     // this lane's head won: pop it
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { bd[i] = bd[i + 1]; bk[i] = bk[i + 1]; }
-            bd[4] = INFINITY; bk[4] = 0x7fffffff;
-        }
-        // neighbour slot r is written by sub-lane r & 3 (unused slots stay zero, :424)
-        if (ok && (r & 3) == q) {
-            float f5[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-            if (mk != 0x7fffffff) {
-                Pose ot; int intent;
-                if (mk < N) { const int j = env * N + mk; ot = Pose{d.ex[j], d.ey[j], d.ev[j], d.eh[j]}; intent = d.route_meta[mk].intent; }
-                else { const int j = env * d.M + (mk - N); ot = Pose{d.nx[j], d.ny[j], d.nv[j], d.nh[j]}; intent = d.route_meta[N + d.nroute[j]].intent; }
-                obs_neighbor_features(me, ot, intent, f5);
+                for (int i = 0; i < 4; ++i) { bd[i] = bd[i + 1]; bk[i] = bk[i + 1]; }
+                bd[4] = INFINITY; bk[4] = 0x7fffffff;
             }
-#pragma unroll
-            for (int i = 0; i < 5; ++i) orow[6 + 5 * r + i] = f5[i];
         }
+    }
+    // The list order above is what a STABLE sort gives.  std::sort (:490) is stable only up to 16 elements; beyond that,
+    // exactly equal distances among the first six ranks are ordered by libstdc++'s introsort — replay it (rare).
+    nbr += __shfl_xor_sync(FULL, nbr, 1, 4);
+    nbr += __shfl_xor_sync(FULL, nbr, 2, 4);
+    if (nbr > stdsort::THRESHOLD) {
+        bool tie = false;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) tie |= (fd[r] == fd[r + 1]) && fd[r + 1] < INFINITY;
+        if (tie) {                                 // quad-uniform; every lane of the quad replays it (no shuffles inside)
+            const unsigned long long ex5 = exact_neighbor_top5(d.ex, d.ey, d.ealive, d.nx, d.ny, N, d.M, env, self, me.x, me.y, nn);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) { const int kk = (int)((ex5 >> (8 * r)) & 0xffu); fk[r] = kk == 0xff ? 0x7fffffff : kk; }
+            if (ok && q == 0) atomicAdd(d.env_stats + (size_t)env * STAT_SLOTS + ST_TIESORT, 1u);
+        }
+    }
+    // neighbour slots 0..3 are written by sub-lanes 0..3 in ONE converged pass (their pose loads overlap), slot 4 by
+    // sub-lane 3 in a second; unused slots stay zero (:424)
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        const int r = it == 0 ? q : (q == 3 ? 4 : -1);
+        if (!ok || r < 0) continue;
+        const int mk = r == 0 ? fk[0] : r == 1 ? fk[1] : r == 2 ? fk[2] : r == 3 ? fk[3] : fk[4];
+        float f5[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (mk != 0x7fffffff) {
+            Pose ot; int intent;
+            if (mk < N) { const int j = env * N + mk; ot = Pose{d.ex[j], d.ey[j], d.ev[j], d.eh[j]}; intent = d.route_meta[mk].intent; }
+            else { const int j = env * d.M + (mk - N); ot = Pose{d.nx[j], d.ny[j], d.nv[j], d.nh[j]}; intent = d.route_meta[N + d.nroute[j]].intent; }
+            obs_neighbor_features(me, ot, intent, f5);
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) orow[6 + 5 * r + i] = f5[i];
     }
     if (ok && q == 1) {                            // the six ego features (:431-458); zeros for a dead ego (:426-429)
         float f6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};

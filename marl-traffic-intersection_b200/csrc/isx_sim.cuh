@@ -551,4 +551,111 @@ ISX_HD void obs_neighbor_features(const Pose& me, const Pose& ot, int intent, fl
     o5[4] = (float)intent;
 }
 
+// ------------------------------------------------------------------------------------------------ neighbour order
+// IntersectionEnv.cpp:490 orders the neighbour list with std::sort and a `dist <` comparator.  std::sort is not stable:
+// when two distances are EXACTLY equal and the list is longer than 16, which of the two comes first is decided by the
+// library's introsort.  The reference "as run here" is libstdc++ 13 (bits/stl_algo.h __sort / __introsort_loop /
+// __final_insertion_sort, bits/stl_heap.h for the depth-limit fallback), so that algorithm is restated below on a
+// permutation p[0..n) of list positions ordered by key[p[i]].  For n <= 16 it degenerates to a stable insertion sort,
+// which is what the fast path of k_features computes; the kernel only comes here when a tie can change the answer.
+namespace stdsort {
+constexpr int THRESHOLD = 16;
+ISX_HD bool lt(const float* key, uint8_t a, uint8_t b) { return key[a] < key[b]; }
+ISX_HD void swp(uint8_t* p, int i, int j) { const uint8_t t = p[i]; p[i] = p[j]; p[j] = t; }
+ISX_HD void sift_up(const float* key, uint8_t* a, int hole, int top, uint8_t val) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && lt(key, a[parent], val)) { a[hole] = a[parent]; hole = parent; parent = (hole - 1) / 2; }
+    a[hole] = val;
+}
+ISX_HD void sift_hole(const float* key, uint8_t* a, int hole, int len, uint8_t val) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (lt(key, a[child], a[child - 1])) --child;
+        a[hole] = a[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        a[hole] = a[child - 1];
+        hole = child - 1;
+    }
+    sift_up(key, a, hole, top, val);
+}
+ISX_HD void heap_sort(const float* key, uint8_t* a, int len) {     // __partial_sort(first, last, last)
+    if (len >= 2)
+        for (int parent = (len - 2) / 2;; --parent) {
+            sift_hole(key, a, parent, len, a[parent]);
+            if (parent == 0) break;
+        }
+    for (int last = len - 1; last >= 1; --last) {
+        const uint8_t val = a[last];
+        a[last] = a[0];
+        sift_hole(key, a, 0, last, val);
+    }
+}
+ISX_HD int partition_pivot(const float* key, uint8_t* p, int first, int last) {
+    const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+    int med;                                        // median of (a, b, c) under `<`, moved to `first`
+    if (lt(key, p[a], p[b])) med = lt(key, p[b], p[c]) ? b : (lt(key, p[a], p[c]) ? c : a);
+    else med = lt(key, p[a], p[c]) ? a : (lt(key, p[b], p[c]) ? c : b);
+    swp(p, first, med);
+    int lo = first + 1, hi = last;
+    for (;;) {
+        while (lo < last && lt(key, p[lo], p[first])) ++lo;        // bounds only matter for NaN keys (UB in the reference)
+        --hi;
+        while (hi > first && lt(key, p[first], p[hi])) --hi;
+        if (!(lo < hi)) return lo;
+        swp(p, lo, hi);
+        ++lo;
+    }
+}
+ISX_HD void linear_insert(const float* key, uint8_t* p, int i, int floor_) {
+    const uint8_t val = p[i];
+    int next = i - 1;
+    while (next >= floor_ && lt(key, val, p[next])) { p[i] = p[next]; i = next; --next; }
+    p[i] = val;
+}
+ISX_HD void insertion(const float* key, uint8_t* p, int first, int last) {
+    for (int i = first + 1; i < last; ++i) {
+        if (lt(key, p[i], p[first])) {
+            const uint8_t val = p[i];
+            for (int j = i; j > first; --j) p[j] = p[j - 1];
+            p[first] = val;
+        } else {
+            linear_insert(key, p, i, first);
+        }
+    }
+}
+// Sorts p[0..n) (caller fills it, normally with the identity); returns how many ranges fell back to the heap sort.
+ISX_HD int sort(const float* key, uint8_t* p, int n) {
+    if (n <= 0) return 0;
+    int heaps = 0;
+    int lg = 0;
+    while ((n >> (lg + 1)) != 0) ++lg;
+    int sf[24], sl[24], sd[24], sp = 0;             // pending (first, last, depth) ranges; they are disjoint, order is free
+    sf[0] = 0; sl[0] = n; sd[0] = 2 * lg; sp = 1;
+    while (sp) {
+        --sp;
+        const int first = sf[sp];
+        int last = sl[sp], depth = sd[sp];
+        while (last - first > THRESHOLD) {
+            if (depth == 0) { heap_sort(key, p + first, last - first); ++heaps; break; }
+            --depth;
+            const int cut = partition_pivot(key, p, first, last);
+            sf[sp] = cut; sl[sp] = last; sd[sp] = depth; ++sp;
+            last = cut;
+        }
+    }
+    if (n > THRESHOLD) {
+        insertion(key, p, 0, THRESHOLD);
+        for (int i = THRESHOLD; i < n; ++i) linear_insert(key, p, i, 0);
+    } else {
+        insertion(key, p, 0, n);
+    }
+    return heaps;
+}
+}  // namespace stdsort
+
 }  // namespace isx

@@ -354,6 +354,90 @@ static void lidar_scan(int lanes, int rays, const float *rel, const car_t *self,
     }
 }
 
+/* ------------------------------------------------------------------ neighbour ordering
+ * IntersectionEnv.cpp:490 is std::sort with `a.dist < b.dist`; with exactly equal distances and more than 16
+ * neighbours the order of the equal ones is whatever the library's introsort leaves.  The reference run here is
+ * libstdc++ 13: bits/stl_algo.h:1918-1952 (__introsort_loop, depth 2*floor(log2 n), threshold 16, median of
+ * first+1 / mid / last-1 swapped to first, __unguarded_partition, then __final_insertion_sort) and
+ * bits/stl_heap.h:135-262,340-430 for the __partial_sort fallback.  Restated on (key, position) records;
+ * pinned against the real std::sort by tests/test_oracle_vs_ref.py::test_neighbor_sort_*. */
+typedef struct { float d; int pos; } nb_t;
+static void nb_push_heap(nb_t *a, int hole, int top, nb_t v) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && a[parent].d < v.d) { a[hole] = a[parent]; hole = parent; parent = (hole - 1) / 2; }
+    a[hole] = v;
+}
+static void nb_adjust_heap(nb_t *a, int hole, int len, nb_t v) {
+    const int top = hole; int second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (a[second].d < a[second - 1].d) second--;
+        a[hole] = a[second]; hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) { second = 2 * (second + 1); a[hole] = a[second - 1]; hole = second - 1; }
+    nb_push_heap(a, hole, top, v);
+}
+static void nb_heapsort(nb_t *a, int len) {
+    if (len >= 2) { int parent = (len - 2) / 2; for (;;) { nb_adjust_heap(a, parent, len, a[parent]); if (parent == 0) break; parent--; } }
+    while (len > 1) { --len; nb_t v = a[len]; a[len] = a[0]; nb_adjust_heap(a, 0, len, v); }
+}
+static void nb_swap(nb_t *x, nb_t *y) { nb_t t = *x; *x = *y; *y = t; }
+static nb_t *nb_partition_pivot(nb_t *first, nb_t *last) {
+    nb_t *a = first + 1, *b = first + (last - first) / 2, *c = last - 1;
+    if (a->d < b->d) { if (b->d < c->d) nb_swap(first, b); else if (a->d < c->d) nb_swap(first, c); else nb_swap(first, a); }
+    else if (a->d < c->d) nb_swap(first, a);
+    else if (b->d < c->d) nb_swap(first, c);
+    else nb_swap(first, b);
+    nb_t *lo = first + 1, *hi = last;
+    for (;;) {
+        while (lo->d < first->d) ++lo;
+        --hi;
+        while (first->d < hi->d) --hi;
+        if (!(lo < hi)) return lo;
+        nb_swap(lo, hi);
+        ++lo;
+    }
+}
+static int g_nb_heaps;
+static void nb_introsort(nb_t *first, nb_t *last, int depth) {
+    while (last - first > 16) {
+        if (depth == 0) { nb_heapsort(first, (int)(last - first)); g_nb_heaps++; return; }
+        --depth;
+        nb_t *cut = nb_partition_pivot(first, last);
+        nb_introsort(cut, last, depth);
+        last = cut;
+    }
+}
+static void nb_linear_insert(nb_t *last) {
+    nb_t v = *last; nb_t *next = last - 1;
+    while (v.d < next->d) { *last = *next; last = next; --next; }
+    *last = v;
+}
+static void nb_insertion(nb_t *first, nb_t *last) {
+    if (first == last) return;
+    for (nb_t *i = first + 1; i != last; ++i) {
+        if (i->d < first->d) { nb_t v = *i; memmove(first + 1, first, (size_t)(i - first) * sizeof(nb_t)); *first = v; }
+        else nb_linear_insert(i);
+    }
+}
+static void nb_sort(nb_t *a, int n) {
+    if (n == 0) return;
+    int lg = 0; while ((n >> (lg + 1)) != 0) ++lg;
+    nb_introsort(a, a + n, 2 * lg);
+    if (n > 16) { nb_insertion(a, a + 16); for (nb_t *i = a + 16; i != a + n; ++i) nb_linear_insert(i); }
+    else nb_insertion(a, a + n);
+}
+int isxo_std_sort(const float *keys, int n, int32_t *perm_out) {
+    nb_t *a = (nb_t *)malloc(sizeof(nb_t) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i) { a[i].d = keys[i]; a[i].pos = i; }
+    g_nb_heaps = 0;
+    nb_sort(a, n);
+    for (int i = 0; i < n; ++i) perm_out[i] = a[i].pos;
+    free(a);
+    return g_nb_heaps;
+}
+
+
 /* ------------------------------------------------------------------ observations */
 /* IntersectionEnv.cpp:418-520 */
 static void observe(const struct isxo_env *e, float *obs) {
@@ -371,7 +455,7 @@ static void observe(const struct isxo_env *e, float *obs) {
             volatile float ny = -dyd, nx = dxd;
             o[5] = wrap_angle(atan2f(ny, nx) - c->h) / PI_F;
         }
-        /* neighbours: other alive egos then NPCs, stable ascending distance (std::sort on <=16 items is an insertion sort) */
+        /* neighbours: other alive egos then NPCs, ordered as libstdc++ std::sort leaves them (nb_sort above) */
         float nd[MAX_AGENTS + MAX_NPC]; const car_t *nc[MAX_AGENTS + MAX_NPC]; int nint[MAX_AGENTS + MAX_NPC]; int m = 0;
         for (int j = 0; j < e->n; ++j) {
             if (j == i || !e->cars[j].alive) continue;
@@ -382,19 +466,17 @@ static void observe(const struct isxo_env *e, float *obs) {
             const float dx = e->npcs[j].x - c->x, dy = e->npcs[j].y - c->y;
             nd[m] = sqrtf(dx * dx + dy * dy); nc[m] = &e->npcs[j]; nint[m] = e->traffic_routes[e->npcs[j].route].intent; m++;
         }
-        for (int a = 1; a < m; ++a) { /* stable insertion sort */
-            const float kd = nd[a]; const car_t *kc = nc[a]; const int ki = nint[a]; int b = a - 1;
-            while (b >= 0 && kd < nd[b]) { nd[b + 1] = nd[b]; nc[b + 1] = nc[b]; nint[b + 1] = nint[b]; --b; }
-            nd[b + 1] = kd; nc[b + 1] = kc; nint[b + 1] = ki;
-        }
+        nb_t ord[MAX_AGENTS + MAX_NPC];
+        for (int a = 0; a < m; ++a) { ord[a].d = nd[a]; ord[a].pos = a; }
+        nb_sort(ord, m);
         const int take = m < 5 ? m : 5;
         for (int k = 0; k < take; ++k) {
             float *q = o + 6 + 5 * k;
-            q[0] = (nc[k]->x - c->x) / (float)W_PX;
-            q[1] = (nc[k]->y - c->y) / (float)H_PX;
-            q[2] = (nc[k]->v - c->v) / MAX_SPEED;
-            q[3] = wrap_angle(nc[k]->h - c->h) / PI_F;
-            q[4] = (float)nint[k];
+            q[0] = (nc[ord[k].pos]->x - c->x) / (float)W_PX;
+            q[1] = (nc[ord[k].pos]->y - c->y) / (float)H_PX;
+            q[2] = (nc[ord[k].pos]->v - c->v) / MAX_SPEED;
+            q[3] = wrap_angle(nc[ord[k].pos]->h - c->h) / PI_F;
+            q[4] = (float)nint[ord[k].pos];
         }
         const float inv = 1.0f / 250.0f; /* Lidar.cpp:92-97 */
         for (int k = 0; k < e->rays && 31 + k < ISX_OBS_DIM; ++k) o[31 + k] = e->lidar[i][k] * inv;

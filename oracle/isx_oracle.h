@@ -31,6 +31,7 @@ int isxo_get_npcs(void *h, isx_car_state *out, int cap);
 int isxo_get_lidar(void *h, int agent, float *dist, int cap);
 void isxo_set_egos(void *h, const isx_car_state *s, int n);
 void isxo_set_npcs(void *h, const isx_car_state *s, int n);
+int isxo_std_sort(const float *keys, int n, int32_t *perm_out);
 long long isxo_rollout(void *h, int steps, float dt, int32_t *status_hist6, double *reward_sum);
 #ifdef __cplusplus
 }

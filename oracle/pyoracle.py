@@ -209,6 +209,22 @@ class _Unit:
         self._f("corners")(_fp(a), _fp(o))
         return o.reshape(4, 2)
 
+    def std_sort(self, keys):
+        """Rank order the library's neighbour sort leaves `keys` in: (perm[int32], heap_fallbacks or None)."""
+        k = np.ascontiguousarray(keys, np.float32)
+        perm = np.zeros(max(k.shape[0], 1), np.int32)
+        f = self._f("std_sort")
+        f.restype = C.c_int if self._p != "isxref_" else None
+        r = f(_fp(k), k.shape[0], _ip(perm))
+        return perm[: k.shape[0]].copy(), r
+
+    def sort_adversary(self, n):
+        out = np.zeros(n, np.float32)
+        f = self._f("sort_adversary")
+        f.restype = None
+        f(int(n), _fp(out))
+        return out
+
     def lidar(self, lanes, rays, self_pose, others):
         sp = np.array(self_pose, np.float32)
         ot = np.ascontiguousarray(np.array(others, np.float32).reshape(-1, 3))

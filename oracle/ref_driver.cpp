@@ -13,6 +13,7 @@
  */
 #include "IntersectionEnv.h"
 
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <map>
@@ -394,6 +395,32 @@ void isxref_libm_tanf(const float *x, int n, float *o) { for (int i = 0; i < n; 
 void isxref_libm_atan2f(const float *y, const float *x, int n, float *o) { for (int i = 0; i < n; ++i) o[i] = std::atan2(y[i], x[i]); }
 void isxref_libm_hypotf(const float *y, const float *x, int n, float *o) { for (int i = 0; i < n; ++i) o[i] = std::hypot(y[i], x[i]); }
 void isxref_libm_fmodf(const float *y, const float *x, int n, float *o) { for (int i = 0; i < n; ++i) o[i] = std::fmod(y[i], x[i]); }
+
+/* The toolchain's std::sort on the element type and comparator of IntersectionEnv.cpp:459-462,490 (a float key and a
+ * pointer payload).  perm_out[i] = original list position of the element that ends at rank i.  Used to pin the
+ * oracle's and the product's restatement of libstdc++ introsort for lists with exactly-equal distances. */
+void isxref_std_sort(const float *keys, int n, int32_t *perm_out) {
+    struct Item { float dist; const void *car; };
+    std::vector<Item> v;
+    static const char base[1] = {0};
+    for (int i = 0; i < n; ++i) v.push_back({keys[i], base + i});
+    std::sort(v.begin(), v.end(), [](const Item &a, const Item &b) { return a.dist < b.dist; });
+    for (int i = 0; i < n; ++i) perm_out[i] = int32_t(static_cast<const char *>(v[size_t(i)].car) - base);
+}
+/* McIlroy's adversary ("A Killer Adversary for Quicksort", 1999) played against this std::sort: returns keys for which
+ * every pivot is nearly the minimum, so that the depth limit is hit and the heap-sort fallback runs. */
+void isxref_sort_adversary(int n, float *keys_out) {
+    const int gas = n;
+    std::vector<int> val(size_t(n), gas), item(static_cast<size_t>(n));
+    int nsolid = 0, candidate = 0;
+    for (int i = 0; i < n; ++i) item[size_t(i)] = i;
+    std::sort(item.begin(), item.end(), [&](int x, int y) {
+        if (val[size_t(x)] == gas && val[size_t(y)] == gas) { if (x == candidate) val[size_t(x)] = nsolid++; else val[size_t(y)] = nsolid++; }
+        if (val[size_t(x)] == gas) candidate = x; else if (val[size_t(y)] == gas) candidate = y;
+        return val[size_t(x)] < val[size_t(y)];
+    });
+    for (int i = 0; i < n; ++i) keys_out[i] = float(val[size_t(i)]);
+}
 
 /* CPU-baseline rollout: `steps` steps with the Philox action stream, reset on terminated|truncated
  * (what a user of env.py does).  Returns agent-steps executed.  Thread-safe per handle. */

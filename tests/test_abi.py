@@ -35,7 +35,7 @@ def test_python_binding_lists_the_same_exports():
 def test_struct_layouts_match_the_header():
     from marl_traffic_intersection_b200 import _lib
     assert C.sizeof(_lib.CarState) == 56 and C.sizeof(_lib.TrafficEvents) == 24
-    assert C.sizeof(_lib.Stats) == 8 * 13
+    assert C.sizeof(_lib.Stats) == 8 * 14
     assert C.sizeof(_lib.Buffers) == 8 * len(_lib._BUF_FIELDS)
     assert _lib.Config.seed.offset % 8 == 0 and C.sizeof(_lib.Config) == _lib.Config.reserved.offset + 4
 

@@ -223,3 +223,89 @@ def test_device_snapshot_restore_replays_bit_exactly():
     assert torch.equal(b.buf["ego_x"][1::2], end_state["ego_x"][1::2]) and torch.equal(b.buf["step"][1::2], end_state["step"][1::2])
     assert (b.buf["step"][::2] == 40).all() and torch.equal(b.buf["obs"][::2], obs_at_save[::2])
     b.close()
+
+
+EDGE = {
+    # sub-warp layouts of k_ego (NP = 1, 2, 4, 8 with padding, 16, 32) and generic beam counts
+    "n2": dict(num_envs=5, num_agents=2, num_lanes=3, ego_routes=R3[:2]),
+    "n5_pad8": dict(num_envs=5, num_agents=5, num_lanes=3, ego_routes=R3[:5], use_team_reward=True, traffic_flow=True, traffic_density=2.0),
+    "n12_np16": dict(num_envs=3, num_agents=12, num_lanes=3, ego_routes=R3, traffic_flow=True, traffic_density=1.0, lidar_rays=72),
+    "rays_33_generic": dict(num_envs=4, num_agents=3, num_lanes=3, ego_routes=R3[3:6], lidar_rays=72, traffic_flow=True, traffic_density=4.0, max_steps=0),
+    "lanes4": dict(num_envs=4, num_agents=4, num_lanes=4, ego_routes=[("IN_1", "OUT_9"), ("IN_6", "OUT_15"), ("IN_11", "OUT_2"), ("IN_16", "OUT_4")],
+                   traffic_flow=True, traffic_density=3.0, traffic_routes=[("IN_2", "OUT_10"), ("IN_7", "OUT_13"), ("IN_12", "OUT_3"), ("IN_13", "OUT_7")]),
+    "lanes1": dict(num_envs=4, num_agents=2, num_lanes=1, ego_routes=[("IN_1", "OUT_3"), ("IN_2", "OUT_1")], traffic_flow=True, traffic_density=3.0,
+                   traffic_routes=[("IN_3", "OUT_1"), ("IN_4", "OUT_2")]),
+    "norespawn_custom_reward": dict(num_envs=6, num_agents=3, num_lanes=3, ego_routes=R3[:3], respawn_enabled=False, max_steps=90, use_team_reward=True,
+                                    reward_config=dict(progress_scale=3.0, stuck_speed_threshold=2.5, stuck_penalty=-0.5, crash_vehicle_penalty=-7.0,
+                                                       crash_object_penalty=-3.0, success_reward=20.0, action_smoothness_scale=-0.3, team_alpha=0.7)),
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE))
+def test_edge_configurations(name):
+    b, refs = make_pair(_benv(), EDGE[name], seed=41)
+    free_run(b, refs, steps=260, seed=41)
+    b.close()
+
+
+@pytest.mark.parametrize("dt", [1.0 / 30.0, 0.0, 0.05])
+def test_per_call_dt(dt):
+    cfg = dict(num_envs=4, num_agents=2, num_lanes=3, ego_routes=R3[4:6], traffic_flow=True, traffic_density=5.0)
+    b, refs = make_pair(_benv(), cfg, seed=43)
+    free_run(b, refs, steps=200, seed=43, dt=dt)
+    b.close()
+
+
+def test_out_of_range_actions_and_dead_egos():
+    """|steer| > 1 drives tanf through its range-reduction branch (Car.cpp:14,28); an ego whose `alive` flag was cleared
+    by the caller (set_state) reports DEAD, done=1, reward 0 and an all-zero obs row (IntersectionEnv.cpp:167-171,426-429)."""
+    import torch
+    from marl_traffic_intersection_b200 import _lib
+    cfg = dict(num_envs=3, num_agents=3, num_lanes=3, ego_routes=R3[:3], use_team_reward=True)
+    b, refs = make_pair(_benv(), cfg, seed=47)
+
+    def wild(obs, t):
+        rng = np.random.default_rng(t)
+        return rng.uniform(-6, 6, (3, 3, 2)).astype(np.float32)
+    free_run(b, refs, steps=120, seed=47, policy=wild)
+    # kill ego 1 of env 2 on both sides
+    eg = refs[2].egos()
+    eg["alive"][1] = 0
+    refs[2].set_egos(eg)
+    ce = (_lib.CarState * 3)()
+    for i, s in enumerate(eg):
+        for f in ("x", "y", "v", "heading", "acc", "steer", "prev_dist", "prev_a0", "prev_a1"):
+            setattr(ce[i], f, float(s[f]))
+        for f in ("path_index", "route", "alive", "uid", "intention"):
+            setattr(ce[i], f, int(s[f]))
+    b.set_env_state(2, ce, None, 0, refs[2].step_count, refs[2].tick)
+    from parity_util import compare_step
+    for t in range(40):
+        act = np.stack([po.philox_actions(47, e, refs[e].tick + 1, 3) for e in range(3)])
+        b.step(torch.from_numpy(act).cuda())
+        outs = [refs[e].step(act[e]) for e in range(3)]
+        compare_step(b, refs, outs, f"dead-ego step {t}")
+        assert outs[2]["status"][1] == po.STATUS_NAMES.index("DEAD") and (outs[2]["obs"][1] == 0).all()
+    b.close()
+
+
+def test_npc_capacity_overflow_is_counted_not_fatal():
+    b = _benv()(dict(num_envs=64, num_agents=1, num_lanes=3, ego_routes=[("IN_6", "OUT_2")], traffic_flow=True, traffic_density=200.0,
+                     npc_capacity=3, seed=5, auto_reset=True))
+    b.rollout(400)
+    st = b.stats()
+    assert st["npc_overflow"] > 0 and int(b.buf["npc_count"].max()) <= 3 and st["agent_steps"] == 64 * 400
+    b.close()
+
+
+@pytest.mark.parametrize("n,cap,density", [(20, 0, 0.0), (20, 16, 3.0), (32, 32, 6.0)])
+def test_equal_distance_neighbours_follow_std_sort(n, cap, density):
+    """More egos than spawn lanes: several egos sit on the same spawn point, so neighbour distances tie exactly while the
+    list is longer than 16 — the regime where IntersectionEnv.cpp:490's std::sort is not stable and the outcome is
+    libstdc++'s introsort.  The device replays that order (k_features -> exact_neighbor_top5) and counts how often."""
+    cfg = dict(num_envs=3, num_agents=n, num_lanes=3, ego_routes=[R3[i % 12] for i in range(n)], traffic_flow=density > 0,
+               traffic_density=density, npc_capacity=cap, max_steps=120)
+    b, refs = make_pair(_benv(), cfg, seed=53)
+    free_run(b, refs, steps=200, seed=53)
+    assert b.stats()["neighbor_tie_sorts"] > 0
+    b.close()

@@ -103,3 +103,53 @@ def test_accelerated_lidar_equals_reference_march():
         rays = 96 if it % 3 else 72
         a, b = c.lidar(L, rays, [x, y, hd], others), h.lidar(L, rays, [x, y, hd], others)
         assert (a == b).all(), (L, rays, x, y, hd, others)
+
+
+def _tie_heavy_keys(rng, n):
+    kind = rng.integers(0, 5)
+    if kind == 0:
+        return rng.integers(0, 3, n).astype(np.float32)                   # two or three distinct values
+    if kind == 1:
+        return rng.integers(0, max(n // 2, 1), n).astype(np.float32)      # many pairs
+    if kind == 2:
+        k = rng.random(n).astype(np.float32)
+        k[rng.integers(0, n, n // 3 + 1)] = k[0]                          # one value repeated among distinct ones
+        return k
+    if kind == 3:
+        return np.sort(rng.integers(0, 8, n)).astype(np.float32)[:: (1 if rng.random() < 0.5 else -1)].copy()
+    return rng.random(n).astype(np.float32)                               # no ties
+
+
+def test_neighbor_sort_matches_the_toolchain_std_sort():
+    """IntersectionEnv.cpp:490 is an UNSTABLE std::sort: with equal distances and > 16 neighbours the outcome is the
+    library's introsort.  Product restatement (isx_sim.cuh stdsort) == oracle restatement == real std::sort."""
+    if not po.have_ref():
+        pytest.skip("needs the compiled reference for std::sort itself")
+    r, o, h = po.ref_unit(), po.oracle_unit(), host()
+    rng = np.random.default_rng(7)
+    for n in list(range(0, 70)) * 30:
+        keys = _tie_heavy_keys(rng, n) if n else np.zeros(0, np.float32)
+        pr, _ = r.std_sort(keys)
+        ph, _ = h.std_sort(keys)
+        pq, _ = o.std_sort(keys)
+        assert (pr == ph).all() and (pr == pq).all(), (n, keys.tolist(), pr.tolist(), ph.tolist())
+        assert sorted(pr.tolist()) == list(range(n)) and (np.diff(keys[pr]) >= 0).all()
+
+
+def test_neighbor_sort_heap_fallback_against_adversary():
+    """McIlroy's adversary drives std::sort to its depth limit; the heap-sort fallback must then agree too."""
+    if not po.have_ref():
+        pytest.skip("needs the compiled reference for std::sort itself")
+    r, o, h = po.ref_unit(), po.oracle_unit(), host()
+    fell_back = 0
+    for n in range(17, 64):
+        base = r.sort_adversary(n)
+        for q in (1, 2, 3):                                               # q > 1 folds the killer sequence into ties
+            keys = np.floor(base / q).astype(np.float32)
+            pr, _ = r.std_sort(keys)
+            ph, nh = h.std_sort(keys)
+            pq, nq = o.std_sort(keys)
+            assert (pr == ph).all() and (pr == pq).all(), (n, q)
+            assert nh == nq
+            fell_back += nh > 0
+    assert fell_back > 0
