@@ -59,10 +59,18 @@ struct isx_handle {
     // pinned staging for isx_step_host
     float* h_actions = nullptr; float* d_actions = nullptr;
     float* h_obs = nullptr; float* h_reward = nullptr;
-    uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;
+    uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;   // views into h_small
+    uint8_t *d_small = nullptr, *h_small = nullptr;      // reward | done | status | terminated | truncated, one block each side
+    size_t small_off[5] = {0, 0, 0, 0, 0}, small_bytes = 0;
     float last_dt = -1.0f, last_prob = 0.0f;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_shard[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_shard[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t pipe_stream = nullptr;                  // the captured host step replays here
+    cudaEvent_t ev_pipe_in = nullptr;
+    cudaGraphExec_t pipe_exec = nullptr;
+    float pipe_dt = 0.0f;
+    bool use_graph = true;
+    int pipe_n = 1, pipe_e0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // env ranges of the host-step pipeline (isx_step_pinned)
     cudaEvent_t ev_copy_done = nullptr;
     std::vector<RouteHost> routes;
 };
@@ -216,8 +224,22 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     ALLOC(d.nx, EM); ALLOC(d.ny, EM); ALLOC(d.nv, EM); ALLOC(d.nh, EM); ALLOC(d.nsteer, EM);
     ALLOC(d.npidx, EM); ALLOC(d.nroute, EM); ALLOC(d.nuid, EM);
     ALLOC(d.ncount, E); ALLOC(d.next_uid, E); ALLOC(d.step_count, E); ALLOC(d.tick, E);
-    ALLOC(d.obs, EN * ISX_OBS_DIM); ALLOC(d.reward, EN); ALLOC(d.done, EN); ALLOC(d.status, EN);
-    ALLOC(d.terminated, E); ALLOC(d.truncated, E); ALLOC(d.agents_alive, E);
+    ALLOC(d.obs, EN * ISX_OBS_DIM); ALLOC(d.agents_alive, E);
+    {
+        // reward | done | status | terminated | truncated live in ONE block (sub-arrays 256 B aligned), mirrored by one
+        // pinned host block, so the host-buffer step brings all of them back with a single copy
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        h->small_off[0] = 0;
+        h->small_off[1] = up(sizeof(float) * EN);
+        h->small_off[2] = h->small_off[1] + up(EN);
+        h->small_off[3] = h->small_off[2] + up(EN);
+        h->small_off[4] = h->small_off[3] + up(E);
+        h->small_bytes = h->small_off[4] + up(E);
+        ALLOC(h->d_small, h->small_bytes);
+        d.reward = reinterpret_cast<float*>(h->d_small + h->small_off[0]);
+        d.done = h->d_small + h->small_off[1]; d.status = h->d_small + h->small_off[2];
+        d.terminated = h->d_small + h->small_off[3]; d.truncated = h->d_small + h->small_off[4];
+    }
     ALLOC(d.lidar_hit, EN * ISX_MAX_RAYS); ALLOC(d.events, E);
     ALLOC(d.env_stats, E * STAT_SLOTS); ALLOC(d.stats, 16);
     ALLOC(h->d_actions, EN * 2);
@@ -254,17 +276,44 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     // pinned staging
     if (cudaMallocHost((void**)&h->h_actions, sizeof(float) * EN * 2) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_obs, sizeof(float) * EN * ISX_OBS_DIM) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_reward, sizeof(float) * EN) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_done, EN) != cudaSuccess || cudaMallocHost((void**)&h->h_status, EN) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_term, E) != cudaSuccess || cudaMallocHost((void**)&h->h_trunc, E) != cudaSuccess) {
+        cudaMallocHost((void**)&h->h_small, h->small_bytes) != cudaSuccess) {
         isx_destroy(h);
         return fail(ISX_E_CUDA, "pinned host allocation failed");
     }
+    h->h_reward = reinterpret_cast<float*>(h->h_small + h->small_off[0]);
+    h->h_done = h->h_small + h->small_off[1]; h->h_status = h->h_small + h->small_off[2];
+    h->h_term = h->h_small + h->small_off[3]; h->h_trunc = h->h_small + h->small_off[4];
     {
         cudaError_t e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_shard[i], cudaEventDisableTiming);
+        for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_shard[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->pipe_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pipe_in, cudaEventDisableTiming);
+        h->use_graph = getenv("ISX_NO_GRAPH") == nullptr;
         if (e != cudaSuccess) { isx_destroy(h); return fail(ISX_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
+    }
+    {
+        // Pipeline plan of the host-buffer step: env ranges whose kernels run while the copy engine drains the previous
+        // range's obs rows.  Measured on B200 + PCIe gen5 (tools/e2e_probe.py): the D2H of obs is 589 us of a 729 us step
+        // at 8192x8; each range costs ~55 us of fixed kernel latency, so few equal ranges beat many or geometric ones.
+        // ISX_PIPE_PLAN="w0,w1,..." (<= 8 weights) overrides, for tuning.
+        int w[8] = {1, 1, 1, 1, 0, 0, 0, 0}, nw = d.E >= 1024 ? 4 : 1;
+        if (const char* plan = getenv("ISX_PIPE_PLAN")) {
+            int k = 0;
+            for (const char* c = plan; *c && k < 8;) {
+                char* endp = nullptr;
+                const long v = std::strtol(c, &endp, 10);
+                if (endp == c) break;
+                if (v > 0) w[k++] = (int)v;
+                c = (*endp == ',') ? endp + 1 : endp;
+            }
+            if (k > 0) nw = k;
+        }
+        long long tot = 0, acc = 0;
+        for (int i = 0; i < nw; ++i) tot += w[i];
+        h->pipe_n = nw;
+        for (int i = 0; i < nw; ++i) { h->pipe_e0[i] = (int)((long long)d.E * acc / tot); acc += w[i]; }
+        h->pipe_e0[nw] = d.E;
     }
     *out = h;
     const int rc = isx_reset(h, nullptr, nullptr);
@@ -278,16 +327,15 @@ int isx_destroy(isx_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    if (h->pipe_exec) cudaGraphExecDestroy(h->pipe_exec);
+    if (h->pipe_stream) cudaStreamDestroy(h->pipe_stream);
+    if (h->ev_pipe_in) cudaEventDestroy(h->ev_pipe_in);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    for (int i = 0; i < 4; ++i) if (h->ev_shard[i]) cudaEventDestroy(h->ev_shard[i]);
+    for (int i = 0; i < 8; ++i) if (h->ev_shard[i]) cudaEventDestroy(h->ev_shard[i]);
     if (h->ev_copy_done) cudaEventDestroy(h->ev_copy_done);
     if (h->h_actions) cudaFreeHost(h->h_actions);
     if (h->h_obs) cudaFreeHost(h->h_obs);
-    if (h->h_reward) cudaFreeHost(h->h_reward);
-    if (h->h_done) cudaFreeHost(h->h_done);
-    if (h->h_status) cudaFreeHost(h->h_status);
-    if (h->h_term) cudaFreeHost(h->h_term);
-    if (h->h_trunc) cudaFreeHost(h->h_trunc);
+    if (h->h_small) cudaFreeHost(h->h_small);
     delete h;
     return ISX_OK;
 }
@@ -409,23 +457,15 @@ static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
     return s;
 }
 
-// Host-buffer step with the device->host copy PIPELINED behind the kernels: the env range is cut into shards; the
-// kernels of shard c+1 run while the copy engine drains the obs rows of shard c (obs is 127 floats per agent — the
-// copy, not the simulation, bounds the end-to-end rate).  Results land in the handle's pinned staging buffers
-// (isx_host_views); actions are taken from the pinned `actions` view.  Synchronous on return.
-int isx_step_pinned(isx_handle* h, float dt, void* stream) {
-    if (!h) return fail(ISX_E_ARG, "null handle");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CK(cudaSetDevice(h->device));
+// Enqueue one pipelined host-buffer step on `st` (+ the handle's copy stream, forked and joined through events).
+static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st) {
     const Dev& d = h->d;
     const size_t EN = (size_t)d.E * d.N;
     const float prob = spawn_prob_for(h, dt);
     CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * EN * 2, cudaMemcpyHostToDevice, st));
-    const int shards = d.E >= 4 * 256 ? 4 : 1;
-    const int per = (d.E + shards - 1) / shards;
-    for (int c = 0; c < shards; ++c) {
-        const int e0 = c * per, cnt = (e0 + per <= d.E) ? per : d.E - e0;
-        if (cnt <= 0) break;
+    for (int c = 0; c < h->pipe_n; ++c) {
+        const int e0 = h->pipe_e0[c], cnt = h->pipe_e0[c + 1] - e0;
+        if (cnt <= 0) continue;
         const Dev sd = shard_of(d, e0, cnt, c);
         const size_t aoff = (size_t)e0 * d.N, an = (size_t)cnt * d.N;
         CK(launch_dynamics(sd, h->d_actions + aoff * 2, dt, prob, st));
@@ -433,15 +473,48 @@ int isx_step_pinned(isx_handle* h, float dt, void* stream) {
         CK(cudaEventRecord(h->ev_shard[c], st));
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_shard[c], 0));
         CK(cudaMemcpyAsync(h->h_obs + aoff * ISX_OBS_DIM, d.obs + aoff * ISX_OBS_DIM, sizeof(float) * an * ISX_OBS_DIM, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaMemcpyAsync(h->h_reward + aoff, d.reward + aoff, sizeof(float) * an, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaMemcpyAsync(h->h_done + aoff, d.done + aoff, an, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaMemcpyAsync(h->h_status + aoff, d.status + aoff, an, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaMemcpyAsync(h->h_term + e0, d.terminated + e0, (size_t)cnt, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaMemcpyAsync(h->h_trunc + e0, d.truncated + e0, (size_t)cnt, cudaMemcpyDeviceToHost, h->copy_stream));
     }
+    // the stream order of copy_stream puts this after the last shard's kernels (its wait on ev_shard[last])
+    CK(cudaMemcpyAsync(h->h_small, h->d_small, h->small_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
     CK(cudaEventRecord(h->ev_copy_done, h->copy_stream));
-    CK(cudaStreamWaitEvent(st, h->ev_copy_done, 0));        // keep the caller's stream ordered after the copies
-    CK(cudaEventSynchronize(h->ev_copy_done));
+    CK(cudaStreamWaitEvent(st, h->ev_copy_done, 0));        // join: `st` is ordered after the copies
+    return ISX_OK;
+}
+
+// Host-buffer step with the device->host copy PIPELINED behind the kernels: the env range is cut into shards; the
+// kernels of shard c+1 run while the copy engine drains the obs rows of shard c (obs is 127 floats per agent — the
+// copy, not the simulation, bounds the end-to-end rate).  Results land in the handle's pinned staging buffers
+// (isx_host_views); actions are taken from the pinned `actions` view.  Synchronous on return.
+// The whole step (1 + shards copies in, 4 kernels and 1 copy out per shard, the fork/join events) is captured ONCE per
+// dt into a CUDA graph and replayed with a single launch: issuing ~35 runtime calls per step from the host costs more
+// than the first shards take to run.  ISX_NO_GRAPH=1 at isx_create keeps the plain stream path.
+int isx_step_pinned(isx_handle* h, float dt, void* stream) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    if (!h->use_graph) {
+        const int rc = enqueue_pinned_step(h, dt, st);
+        if (rc) return rc;
+        CK(cudaEventSynchronize(h->ev_copy_done));
+        return ISX_OK;
+    }
+    if (!h->pipe_exec || std::memcmp(&h->pipe_dt, &dt, sizeof dt) != 0) {
+        if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(h->pipe_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_pinned_step(h, dt, h->pipe_stream);
+        const cudaError_t ce = cudaStreamEndCapture(h->pipe_stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        CK(ce);
+        const cudaError_t ie = cudaGraphInstantiate(&h->pipe_exec, g, 0);
+        cudaGraphDestroy(g);
+        CK(ie);
+        h->pipe_dt = dt;
+    }
+    CK(cudaEventRecord(h->ev_pipe_in, st));                  // order the replay after whatever the caller queued on `st`
+    CK(cudaStreamWaitEvent(h->pipe_stream, h->ev_pipe_in, 0));
+    CK(cudaGraphLaunch(h->pipe_exec, h->pipe_stream));
+    CK(cudaStreamSynchronize(h->pipe_stream));
     return ISX_OK;
 }
 

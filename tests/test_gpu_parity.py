@@ -139,7 +139,9 @@ def test_state_injection_roundtrip_and_resync():
 
 def test_pipelined_host_step_equals_device_step():
     """isx_step_pinned cuts the env range into 4 shards and overlaps their device->host copies with the next shard's
-    kernels; results must be identical to the single-launch device step (and therefore to the checker)."""
+    kernels, replaying the whole step from a CUDA graph captured per dt; results must be identical to the single-launch
+    device step (and therefore to the checker), also when dt changes between calls (graph re-captured) and when device
+    steps are interleaved on the caller's stream."""
     import torch
     cfg = dict(num_envs=1024, num_agents=3, num_lanes=3, ego_routes=[("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")],
                use_team_reward=True, traffic_flow=True, traffic_density=2.0, seed=21)
@@ -147,8 +149,13 @@ def test_pipelined_host_step_equals_device_step():
     rng = np.random.default_rng(0)
     for t in range(60):
         act = rng.uniform(-1, 1, (1024, 3, 2)).astype(np.float32)
-        obs_d, rew_d, term_d, trunc_d, info = a_env.step(torch.from_numpy(act).cuda())
-        obs_h, rew_h, done_h, status_h, term_h, trunc_h = b_env.step_host(act)
+        dt = (1.0 / 60.0, 1.0 / 60.0, 1.0 / 30.0, 0.02)[(t // 5) % 4]
+        obs_d, rew_d, term_d, trunc_d, info = a_env.step(torch.from_numpy(act).cuda(), dt)
+        if t % 7 == 3:                     # a device-buffer step in between: the replay must stay ordered behind it
+            b_env.step(torch.from_numpy(act).cuda(), dt)
+            act = -act
+            obs_d, rew_d, term_d, trunc_d, info = a_env.step(torch.from_numpy(act).cuda(), dt)
+        obs_h, rew_h, done_h, status_h, term_h, trunc_h = b_env.step_host(act, dt)
         torch.cuda.synchronize()
         assert (obs_d.cpu().numpy().view(np.uint32) == obs_h.view(np.uint32)).all(), t
         assert (rew_d.cpu().numpy().view(np.uint32) == rew_h.view(np.uint32)).all(), t
