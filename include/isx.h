@@ -25,6 +25,7 @@ extern "C" {
 #define ISX_OBS_DIM 127          /* IntersectionEnv.cpp:424 : 6 ego + 5x5 neighbours + 96 lidar */
 #define ISX_PATH_LEN 160         /* RouteGen.cpp:111-205: 50 + 60 + 50 way-points */
 #define ISX_MAX_AGENTS 32        /* egos per env */
+#define ISX_MAX_GROUPS 64         /* config groups of one heterogeneous batch (isx_create_groups) */
 #define ISX_MAX_NPC 32           /* NPC slots per env (reference is unbounded; observed max 13) */
 #define ISX_MAX_RAYS 96
 #define ISX_MAX_ROUTES 64        /* traffic routes */
@@ -133,6 +134,15 @@ int isx_abi_version(void);
  * cannot have ragged N, so here that is ISX_E_ROUTE_START.  Unknown end id: std::out_of_range ->
  * IndexError in the reference (RouteGen.cpp:120) -> ISX_E_ROUTE_END here. */
 int isx_create(const isx_config *cfg, isx_handle **out);
+/* Heterogeneous batch (per-env routes / density / reward weights / lane count in one batch):
+ * group g owns envs [first_g, first_g + cfgs[g].num_envs) of ONE set of buffers (obs [sum E][N][127], ...) and is
+ * stepped with cfgs[g]'s own settings — what N separately configured IntersectionEnv objects are in the reference
+ * (IntersectionEnv.h:27-35, env.py:111-131).  Each group keeps its own seed / env_id_base, so it evolves exactly
+ * like a stand-alone batch created from cfgs[g].  device, num_agents, lidar_rays and (for groups with traffic)
+ * npc_capacity must agree across groups.  isx_create(cfg) == isx_create_groups(cfg, 1). */
+int isx_create_groups(const isx_config *cfgs, int32_t n_groups, isx_handle **out);
+int isx_num_groups(isx_handle *h);
+int isx_group_range(isx_handle *h, int32_t group, int32_t *first_env, int32_t *num_envs);
 int isx_destroy(isx_handle *h);
 
 /* reset() + add_car_with_route (IntersectionEnv.cpp:66-131) for the envs whose mask byte is non-zero

@@ -69,7 +69,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = [
-    "isx_last_error", "isx_abi_version", "isx_create", "isx_destroy", "isx_reset", "isx_step", "isx_step_host",
+    "isx_last_error", "isx_abi_version", "isx_create", "isx_create_groups", "isx_num_groups", "isx_group_range", "isx_destroy", "isx_reset", "isx_step", "isx_step_host",
     "isx_step_pinned", "isx_host_views",
     "isx_rollout", "isx_rollout_timed", "isx_rollout_timed4", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
     "isx_observe", "isx_snapshot_create", "isx_snapshot_save", "isx_snapshot_restore", "isx_snapshot_destroy",
@@ -96,6 +96,9 @@ def load_library(path: str | None = None):
     lib.isx_last_error.argtypes = []
     lib.isx_abi_version.restype = C.c_int
     lib.isx_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.isx_create_groups.argtypes = [C.POINTER(Config), i32, C.POINTER(vp)]
+    lib.isx_num_groups.argtypes = [vp]
+    lib.isx_group_range.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.isx_destroy.argtypes = [vp]
     lib.isx_reset.argtypes = [vp, vp, vp]
     lib.isx_step.argtypes = [vp, vp, f32, vp]

@@ -38,64 +38,93 @@ def _strarr(items: Sequence[str]):
 class BatchedIntersectionEnv:
     """config keys (all optional): num_envs, num_agents, num_lanes, ego_routes, use_team_reward,
     respawn_enabled, max_steps, traffic_flow, traffic_density, traffic_routes, reward_config, lidar_rays (96|72),
-    npc_capacity, seed, device, env_id_base, auto_reset."""
+    npc_capacity, seed, device, env_id_base, auto_reset.
 
-    def __init__(self, config: Optional[Dict[str, Any]] = None):
-        cfg = dict(config or {})
+    ``config`` may also be a LIST of such dicts: a heterogeneous batch whose env range is the concatenation of the
+    groups (isx_create_groups) — routes, lane count, traffic, reward weights and episode settings per group, one set of
+    [sum(num_envs), N, ...] tensors.  ``group_ranges`` lists (first_env, num_envs) per group."""
+
+    def __init__(self, config=None):
+        cfgs = [dict(c) for c in config] if isinstance(config, (list, tuple)) else [dict(config or {})]
+        if not cfgs:
+            raise ValueError("empty config list")
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedIntersectionEnv needs a CUDA device: there is no CPU fallback")
         self._lib = _lib.load_library()
-        self.num_envs = int(cfg.get("num_envs", 1))
-        self.num_lanes = int(cfg.get("num_lanes", 3))
-        self.traffic_flow = bool(cfg.get("traffic_flow", False))
-        self.num_agents = int(cfg.get("num_agents", 1))
-        routes = cfg.get("ego_routes", None)
-        if routes is None:
-            routes = default_ego_routes(self.num_agents, self.num_lanes)   # env.py:138-145
-        routes = [(str(a), str(b)) for a, b in routes]
-        if len(routes) != self.num_agents:
-            raise ValueError(f"ego_routes has {len(routes)} entries for num_agents={self.num_agents}")
-        self.ego_routes = routes
-        troutes = cfg.get("traffic_routes", None)
-        if troutes is None:
-            troutes = all_default_routes(self.num_lanes)                   # env.py:118-123
-        self.traffic_routes = [(str(a), str(b)) for a, b in troutes]
-        dev = cfg.get("device", None)
+        dev = cfgs[0].get("device", None)
         self.device_index = torch.cuda.current_device() if dev is None else torch.device(dev).index or 0
         self.device = torch.device("cuda", self.device_index)
-        self.lidar_rays = int(cfg.get("lidar_rays", 96))
-        self.max_steps = int(cfg.get("max_steps", 2000))
-
-        c = _lib.Config()
-        c.abi_version = _lib.ISX_ABI_VERSION
-        c.device = self.device_index
-        c.num_envs = self.num_envs
-        c.num_agents = self.num_agents
-        c.num_lanes = self.num_lanes
-        c.lidar_rays = self.lidar_rays
-        c.npc_capacity = int(cfg.get("npc_capacity", 16))
-        c.use_team_reward = int(bool(cfg.get("use_team_reward", False)))
-        c.respawn_enabled = int(bool(cfg.get("respawn_enabled", True)))
-        c.max_steps = self.max_steps
-        c.traffic_flow = int(self.traffic_flow)
-        c.traffic_density = float(cfg.get("traffic_density", 0.5))
-        for i, v in enumerate(reward_vector(cfg.get("reward_config", None))):
-            c.reward[i] = v
-        self._keep = [_strarr([a for a, _ in routes]), _strarr([b for _, b in routes]),
-                      _strarr([a for a, _ in self.traffic_routes]), _strarr([b for _, b in self.traffic_routes])]
-        c.ego_start, c.ego_end = self._keep[0], self._keep[1]
-        c.num_traffic_routes = len(self.traffic_routes)
-        c.traffic_start, c.traffic_end = self._keep[2], self._keep[3]
-        c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
-        c.env_id_base = int(cfg.get("env_id_base", 0))
-        c.auto_reset = int(bool(cfg.get("auto_reset", False)))
+        arr = (_lib.Config * len(cfgs))()
+        self._keep = []
+        self.group_configs = []
+        for g, cfg in enumerate(cfgs):
+            self.group_configs.append(self._fill_config(arr[g], cfg))
+        g0 = self.group_configs[0]
+        self.num_envs = sum(gc["num_envs"] for gc in self.group_configs)
+        self.num_agents = g0["num_agents"]
+        self.num_lanes = g0["num_lanes"]
+        self.lidar_rays = g0["lidar_rays"]
+        self.max_steps = g0["max_steps"]
+        self.ego_routes = g0["ego_routes"]
+        self.traffic_routes = g0["traffic_routes"]
+        self.traffic_flow = any(gc["traffic_flow"] for gc in self.group_configs)
         self._h = C.c_void_p()
-        rc = self._lib.isx_create(C.byref(c), C.byref(self._h))
+        if len(cfgs) == 1:
+            rc = self._lib.isx_create(C.byref(arr[0]), C.byref(self._h))
+        else:
+            rc = self._lib.isx_create_groups(arr, len(cfgs), C.byref(self._h))
         if rc == _lib.E_ROUTE_END:
             raise IndexError(self._lib.isx_last_error().decode())       # std::out_of_range -> IndexError in the reference
         _lib.check(self._lib, rc)
-        self.npc_capacity = c.npc_capacity if self.traffic_flow else 1
+        caps = [gc["npc_capacity"] for gc in self.group_configs if gc["traffic_flow"]]
+        self.npc_capacity = caps[0] if caps else 1
+        self.group_ranges = []
+        for g in range(len(cfgs)):
+            a, b = C.c_int32(), C.c_int32()
+            _lib.check(self._lib, self._lib.isx_group_range(self._h, g, C.byref(a), C.byref(b)))
+            self.group_ranges.append((a.value, b.value))
         self._wrap_buffers()
+
+    def _fill_config(self, c, cfg: Dict[str, Any]) -> Dict[str, Any]:
+        """One isx_config from one config dict (defaults of env.py:41-78,111-145); returns the resolved settings."""
+        num_lanes = int(cfg.get("num_lanes", 3))
+        num_agents = int(cfg.get("num_agents", 1))
+        routes = cfg.get("ego_routes", None)
+        if routes is None:
+            routes = default_ego_routes(num_agents, num_lanes)             # env.py:138-145
+        routes = [(str(a), str(b)) for a, b in routes]
+        if len(routes) != num_agents:
+            raise ValueError(f"ego_routes has {len(routes)} entries for num_agents={num_agents}")
+        troutes = cfg.get("traffic_routes", None)
+        if troutes is None:
+            troutes = all_default_routes(num_lanes)                        # env.py:118-123
+        troutes = [(str(a), str(b)) for a, b in troutes]
+        c.abi_version = _lib.ISX_ABI_VERSION
+        c.device = self.device_index
+        c.num_envs = int(cfg.get("num_envs", 1))
+        c.num_agents = num_agents
+        c.num_lanes = num_lanes
+        c.lidar_rays = int(cfg.get("lidar_rays", 96))
+        c.npc_capacity = int(cfg.get("npc_capacity", 16))
+        c.use_team_reward = int(bool(cfg.get("use_team_reward", False)))
+        c.respawn_enabled = int(bool(cfg.get("respawn_enabled", True)))
+        c.max_steps = int(cfg.get("max_steps", 2000))
+        c.traffic_flow = int(bool(cfg.get("traffic_flow", False)))
+        c.traffic_density = float(cfg.get("traffic_density", 0.5))
+        for i, v in enumerate(reward_vector(cfg.get("reward_config", None))):
+            c.reward[i] = v
+        keep = [_strarr([a for a, _ in routes]), _strarr([b for _, b in routes]),
+                _strarr([a for a, _ in troutes]), _strarr([b for _, b in troutes])]
+        self._keep.append(keep)
+        c.ego_start, c.ego_end = keep[0], keep[1]
+        c.num_traffic_routes = len(troutes)
+        c.traffic_start, c.traffic_end = keep[2], keep[3]
+        c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
+        c.env_id_base = int(cfg.get("env_id_base", 0))
+        c.auto_reset = int(bool(cfg.get("auto_reset", False)))
+        return dict(num_envs=c.num_envs, num_agents=num_agents, num_lanes=num_lanes, lidar_rays=c.lidar_rays,
+                    max_steps=c.max_steps, ego_routes=routes, traffic_routes=troutes, traffic_flow=bool(c.traffic_flow),
+                    npc_capacity=c.npc_capacity if c.npc_capacity > 0 else 16)
 
     # ------------------------------------------------------------------ buffers
     def _wrap_buffers(self):

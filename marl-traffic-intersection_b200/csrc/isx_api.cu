@@ -51,8 +51,18 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 struct isx_handle {
-    Dev d{};
-    isx_config cfg{};
+    // One homogeneous slice of the batch (isx_create_groups): its own settings / tables over an env range of the buffers.
+    struct Group {
+        Dev d{};
+        isx_config cfg{};
+        std::vector<RouteHost> routes;
+        int first = 0;                                   // first env of the group in the whole batch
+        float last_dt = -1.0f, last_prob = 0.0f;
+    };
+    struct Piece { int group, e0, cnt; };                // env range (relative to its group) of the host-step pipeline
+    Dev d{};                                             // the whole batch (buffers; group 0's settings)
+    std::vector<Group> groups;
+    std::vector<Piece> pipe;
     int device = 0;
     int lidar_grid = 0;
     std::vector<void*> allocs;
@@ -62,18 +72,37 @@ struct isx_handle {
     uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;   // views into h_small
     uint8_t *d_small = nullptr, *h_small = nullptr;      // reward | done | status | terminated | truncated, one block each side
     size_t small_off[5] = {0, 0, 0, 0, 0}, small_bytes = 0;
-    float last_dt = -1.0f, last_prob = 0.0f;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_shard[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_shard;                   // one per pipeline piece
     cudaStream_t pipe_stream = nullptr;                  // the captured host step replays here
     cudaEvent_t ev_pipe_in = nullptr;
     cudaGraphExec_t pipe_exec = nullptr;
     float pipe_dt = 0.0f;
     bool use_graph = true;
-    int pipe_n = 1, pipe_e0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // env ranges of the host-step pipeline (isx_step_pinned)
     cudaEvent_t ev_copy_done = nullptr;
-    std::vector<RouteHost> routes;
 };
+// A view of envs [e0, e0+cnt) of the same buffers: every per-env array is contiguous per env, so a shard is the same
+// struct with advanced pointers; RNG stays keyed by the global env id through env_base.
+static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
+    Dev s = d;
+    const size_t oE = (size_t)e0, oEN = oE * d.N, oEM = oE * d.M, oEC = oE * (size_t)(d.N + d.M);
+    s.E = cnt; s.env_base = d.env_base + e0;
+    s.ex += oEN; s.ey += oEN; s.ev += oEN; s.eh += oEN; s.esteer += oEN; s.eacc += oEN; s.epd += oEN; s.epa0 += oEN; s.epa1 += oEN;
+    s.epidx += oEN; s.ealive += oEN;
+    s.nx += oEM; s.ny += oEM; s.nv += oEM; s.nh += oEM; s.nsteer += oEM; s.npidx += oEM; s.nroute += oEM; s.nuid += oEM;
+    s.ncount += oE; s.next_uid += oE; s.step_count += oE; s.tick += oE;
+    s.agent_rec = static_cast<char*>(d.agent_rec) + oEN * 16; s.car_rect = static_cast<char*>(d.car_rect) + oEC * 16;
+    s.cand += oEN * (size_t)(d.N + d.M); s.cand_n += oEN; s.ray_counter = d.ray_counter + shard_idx;
+    s.obs += oEN * ISX_OBS_DIM; s.reward += oEN; s.done += oEN; s.status += oEN;
+    s.terminated += oE; s.truncated += oE; s.agents_alive += oE; s.lidar_hit += oEN * ISX_MAX_RAYS;
+    s.events += oE; s.env_stats += oE * STAT_SLOTS;
+    return s;
+}
+
+static isx_handle::Group& group_of(isx_handle* h, int env) {
+    for (auto& g : h->groups) if (env < g.first + g.d.E) return g;
+    return h->groups.back();
+}
 
 template <class T>
 static int dev_alloc(isx_handle* h, T** p, size_t n, bool zero = true) {
@@ -142,9 +171,8 @@ int isx_route(int32_t lanes, const char* start, const char* end, float* path_xy,
     return PATH_LEN;
 }
 
-int isx_create(const isx_config* cfg, isx_handle** out) {
-    if (!cfg || !out) return fail(ISX_E_ARG, "null argument");
-    *out = nullptr;
+// Validates one config and fills the configuration half of a Dev (no pointers yet).
+static int config_to_dev(const isx_config* cfg, Dev& d) {
     if (cfg->abi_version != ISX_ABI_VERSION) return fail(ISX_E_ARG, "abi_version %d != %d", cfg->abi_version, ISX_ABI_VERSION);
     if (cfg->num_envs < 1) return fail(ISX_E_ARG, "num_envs must be >= 1");
     if (cfg->num_agents < 1 || cfg->num_agents > ISX_MAX_AGENTS) return fail(ISX_E_ARG, "num_agents must be in [1,%d]", ISX_MAX_AGENTS);
@@ -152,18 +180,7 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     if (cfg->lidar_rays < 1 || cfg->lidar_rays > ISX_MAX_RAYS) return fail(ISX_E_ARG, "lidar_rays must be in [1,%d]", ISX_MAX_RAYS);
     if (cfg->npc_capacity < 0 || cfg->npc_capacity > ISX_MAX_NPC) return fail(ISX_E_ARG, "npc_capacity must be in [0,%d]", ISX_MAX_NPC);
     if (cfg->num_traffic_routes < 0 || cfg->num_traffic_routes > ISX_MAX_ROUTES) return fail(ISX_E_ARG, "num_traffic_routes must be in [0,%d]", ISX_MAX_ROUTES);
-    if ((long long)cfg->num_envs * cfg->num_agents * ISX_MAX_RAYS >= (1ll << 31)) return fail(ISX_E_ARG, "num_envs * num_agents too large (beam index must fit 31 bits)");
     if (!cfg->ego_start || !cfg->ego_end) return fail(ISX_E_ARG, "ego routes missing");
-
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ISX_E_CUDA, "no CUDA device: this library has no CPU path");
-    if (cfg->device < 0 || cfg->device >= ndev) return fail(ISX_E_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
-    CK(cudaSetDevice(cfg->device));
-
-    isx_handle* h = new isx_handle();
-    h->cfg = *cfg;
-    h->device = cfg->device;
-    Dev& d = h->d;
     d.E = cfg->num_envs; d.N = cfg->num_agents; d.M = cfg->traffic_flow ? (cfg->npc_capacity > 0 ? cfg->npc_capacity : 16) : 1;
     d.R = cfg->lidar_rays; d.lanes = cfg->num_lanes;
     d.use_team = cfg->use_team_reward != 0; d.respawn = cfg->respawn_enabled != 0; d.max_steps = cfg->max_steps;
@@ -171,30 +188,48 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     d.rc = RewardCfg{cfg->reward[0], cfg->reward[1], cfg->reward[2], cfg->reward[3], cfg->reward[4], cfg->reward[5], cfg->reward[6], cfg->reward[7]};
     d.max_progress = hypotf_((float)WIDTH, (float)HEIGHT);
     d.seed = cfg->seed; d.env_base = cfg->env_id_base;
-    if (d.traffic && d.T > 0 && (!cfg->traffic_start || !cfg->traffic_end)) { delete h; return fail(ISX_E_ARG, "traffic routes missing"); }
+    if (d.traffic && d.T > 0 && (!cfg->traffic_start || !cfg->traffic_end)) return fail(ISX_E_ARG, "traffic routes missing");
+    return ISX_OK;
+}
 
-    // ---- route LUT: ego slots then traffic routes
-    const int nroutes = d.N + d.T;
-    h->routes.resize((size_t)nroutes);
-    for (int i = 0; i < nroutes; ++i) {
-        const char* s = i < d.N ? cfg->ego_start[i] : cfg->traffic_start[i - d.N];
-        const char* e = i < d.N ? cfg->ego_end[i] : cfg->traffic_end[i - d.N];
-        if (!s || !e) { delete h; return fail(ISX_E_ARG, "null lane id in route %d", i); }
-        const int rc = build_route(d.lanes, s, e, &h->routes[(size_t)i]);
-        if (rc == -1) { delete h; return fail(ISX_E_ROUTE_START, "unknown start lane id '%s' (route %d)", s, i); }
-        if (rc == -2) { delete h; return fail(ISX_E_ROUTE_END, "unknown end lane id '%s' (route %d)", e, i); }
+int isx_create(const isx_config* cfg, isx_handle** out) { return isx_create_groups(cfg, 1, out); }
+
+// A heterogeneous batch: group g owns the envs [first_g, first_g + cfgs[g].num_envs) of ONE set of buffers and is stepped
+// with its own routes / lanes / traffic / reward / episode settings (its own constant tables and kernel launches).
+// Every group keeps its own seed and env_id_base, so a group evolves bit-for-bit like a stand-alone batch created from
+// the same config.  The groups must agree on what shapes the shared buffers: device, num_agents, lidar_rays, and — for
+// the groups with traffic — npc_capacity.
+int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out) {
+    if (!cfgs || !out) return fail(ISX_E_ARG, "null argument");
+    *out = nullptr;
+    if (n_groups < 1 || n_groups > ISX_MAX_GROUPS) return fail(ISX_E_ARG, "n_groups must be in [1,%d]", ISX_MAX_GROUPS);
+    std::vector<Dev> gd((size_t)n_groups);
+    long long total_envs = 0;
+    int M_all = 1;
+    for (int g = 0; g < n_groups; ++g) {
+        const int rc = config_to_dev(&cfgs[g], gd[(size_t)g]);
+        if (rc) return rc;
+        const isx_config& c = cfgs[g];
+        if (c.device != cfgs[0].device || c.num_agents != cfgs[0].num_agents || c.lidar_rays != cfgs[0].lidar_rays)
+            return fail(ISX_E_ARG, "group %d: device, num_agents and lidar_rays must be the same in every group", g);
+        if (gd[(size_t)g].traffic) {
+            if (M_all != 1 && gd[(size_t)g].M != M_all) return fail(ISX_E_ARG, "group %d: npc_capacity must be the same in every group with traffic", g);
+            M_all = gd[(size_t)g].M;
+        }
+        total_envs += c.num_envs;
     }
-    std::vector<F2> paths((size_t)nroutes * PATH_LEN);
-    std::vector<RouteMeta> meta((size_t)nroutes);
-    for (int i = 0; i < nroutes; ++i) {
-        const RouteHost& r = h->routes[(size_t)i];
-        std::memcpy(&paths[(size_t)i * PATH_LEN], r.path, sizeof(F2) * PATH_LEN);
-        meta[(size_t)i] = RouteMeta{r.spawn_x, r.spawn_y, r.spawn_h, r.intent, r.path[PATH_LEN - 1], r.path[PATH_LEN - 2]};
-    }
-    RoadTables rt;
-    if (!build_road_tables(d.lanes, &rt)) { delete h; return fail(ISX_E_STATE, "road map is not mirror-symmetric"); }
-    std::vector<float> rel((size_t)ISX_MAX_RAYS, 0.0f);
-    lidar_rel_angles(d.R, rel.data());
+    if (total_envs * cfgs[0].num_agents * ISX_MAX_RAYS >= (1ll << 31)) return fail(ISX_E_ARG, "num_envs * num_agents too large (beam index must fit 31 bits)");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ISX_E_CUDA, "no CUDA device: this library has no CPU path");
+    if (cfgs[0].device < 0 || cfgs[0].device >= ndev) return fail(ISX_E_ARG, "device %d out of range (%d devices)", cfgs[0].device, ndev);
+    CK(cudaSetDevice(cfgs[0].device));
+
+    isx_handle* h = new isx_handle();
+    h->device = cfgs[0].device;
+    Dev& d = h->d;                      // the whole batch: group 0's settings, every env, the shared stride M
+    d = gd[0];
+    d.E = (int)total_envs; d.M = M_all;
 
 #define ALLOC(ptr, n)                                     \
     do {                                                  \
@@ -207,17 +242,52 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
         if (e_ != cudaSuccess) { isx_destroy(h); return fail(ISX_E_CUDA, "upload failed: %s", cudaGetErrorString(e_)); } \
     } while (0)
 
-    F2* d_paths; RouteMeta* d_meta; uint32_t* d_bits; uint8_t* d_skip; float* d_rel;
-    ALLOC(d_paths, paths.size()); UPLOAD(d_paths, paths.data(), sizeof(F2) * paths.size());
-    ALLOC(d_meta, meta.size()); UPLOAD(d_meta, meta.data(), sizeof(RouteMeta) * meta.size());
-    rt.bits.resize(road_bits_bytes() / 4, 0u);        // padded to 16 B multiples for the kernel's vector copy
-    rt.skip.resize(road_skip_bytes(), 0);
-    ALLOC(d_bits, rt.bits.size()); UPLOAD(d_bits, rt.bits.data(), sizeof(uint32_t) * rt.bits.size());
-    ALLOC(d_skip, rt.skip.size()); UPLOAD(d_skip, rt.skip.data(), rt.skip.size());
-    ALLOC(d_rel, rel.size()); UPLOAD(d_rel, rel.data(), sizeof(float) * rel.size());
-    d.route_path = d_paths; d.route_meta = d_meta; d.road_bits = d_bits; d.road_skip = d_skip; d.rel_angle = d_rel;
-    d.box_lo = rt.box_lo; d.box_hi = rt.box_hi;
+    // ---- per-group constant tables: route LUT (ego slots then traffic routes), folded road map of its lane count
+    h->groups.resize((size_t)n_groups);
+    float* d_rel = nullptr;
+    {
+        std::vector<float> rel((size_t)ISX_MAX_RAYS, 0.0f);
+        lidar_rel_angles(d.R, rel.data());
+        ALLOC(d_rel, rel.size()); UPLOAD(d_rel, rel.data(), sizeof(float) * rel.size());
+    }
+    for (int g = 0; g < n_groups; ++g) {
+        isx_handle::Group& grp = h->groups[(size_t)g];
+        const isx_config* cfg = &cfgs[g];
+        Dev& q = gd[(size_t)g];
+        grp.cfg = *cfg;
+        const int nroutes = q.N + q.T;
+        grp.routes.resize((size_t)nroutes);
+        for (int i = 0; i < nroutes; ++i) {
+            const char* s = i < q.N ? cfg->ego_start[i] : cfg->traffic_start[i - q.N];
+            const char* e = i < q.N ? cfg->ego_end[i] : cfg->traffic_end[i - q.N];
+            if (!s || !e) { isx_destroy(h); return fail(ISX_E_ARG, "null lane id in route %d", i); }
+            const int rc = build_route(q.lanes, s, e, &grp.routes[(size_t)i]);
+            if (rc == -1) { isx_destroy(h); return fail(ISX_E_ROUTE_START, "unknown start lane id '%s' (route %d)", s, i); }
+            if (rc == -2) { isx_destroy(h); return fail(ISX_E_ROUTE_END, "unknown end lane id '%s' (route %d)", e, i); }
+        }
+        std::vector<F2> paths((size_t)nroutes * PATH_LEN);
+        std::vector<RouteMeta> meta((size_t)nroutes);
+        for (int i = 0; i < nroutes; ++i) {
+            const RouteHost& r = grp.routes[(size_t)i];
+            std::memcpy(&paths[(size_t)i * PATH_LEN], r.path, sizeof(F2) * PATH_LEN);
+            meta[(size_t)i] = RouteMeta{r.spawn_x, r.spawn_y, r.spawn_h, r.intent, r.path[PATH_LEN - 1], r.path[PATH_LEN - 2]};
+        }
+        RoadTables rt;
+        if (!build_road_tables(q.lanes, &rt)) { isx_destroy(h); return fail(ISX_E_STATE, "road map is not mirror-symmetric"); }
+        F2* d_paths; RouteMeta* d_meta; uint32_t* d_bits; uint8_t* d_skip;
+        ALLOC(d_paths, paths.size()); UPLOAD(d_paths, paths.data(), sizeof(F2) * paths.size());
+        ALLOC(d_meta, meta.size()); UPLOAD(d_meta, meta.data(), sizeof(RouteMeta) * meta.size());
+        rt.bits.resize(road_bits_bytes() / 4, 0u);        // padded to 16 B multiples for the kernel's vector copy
+        rt.skip.resize(road_skip_bytes(), 0);
+        ALLOC(d_bits, rt.bits.size()); UPLOAD(d_bits, rt.bits.data(), sizeof(uint32_t) * rt.bits.size());
+        ALLOC(d_skip, rt.skip.size()); UPLOAD(d_skip, rt.skip.data(), rt.skip.size());
+        q.route_path = d_paths; q.route_meta = d_meta; q.road_bits = d_bits; q.road_skip = d_skip; q.rel_angle = d_rel;
+        q.box_lo = rt.box_lo; q.box_hi = rt.box_hi;
+    }
+    d.route_path = gd[0].route_path; d.route_meta = gd[0].route_meta; d.road_bits = gd[0].road_bits; d.road_skip = gd[0].road_skip;
+    d.rel_angle = d_rel; d.box_lo = gd[0].box_lo; d.box_hi = gd[0].box_hi;
 
+    // ---- state, scratch and output buffers, shared by all groups
     const size_t EN = (size_t)d.E * d.N, EM = (size_t)d.E * d.M, E = (size_t)d.E;
     ALLOC(d.ex, EN); ALLOC(d.ey, EN); ALLOC(d.ev, EN); ALLOC(d.eh, EN); ALLOC(d.esteer, EN); ALLOC(d.eacc, EN);
     ALLOC(d.epd, EN); ALLOC(d.epa0, EN); ALLOC(d.epa1, EN); ALLOC(d.epidx, EN); ALLOC(d.ealive, EN);
@@ -246,11 +316,29 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     if (getenv("ISX_TRACE")) ALLOC(d.trace, E * 16); else d.trace = nullptr;
     {
         float4* rec; int4* rc;
-        ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN); ALLOC(d.ray_counter, 8);
+        ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN);
+        ALLOC(d.ray_counter, ISX_MAX_GROUPS + 8);
         d.agent_rec = rec; d.car_rect = rc;
     }
 #undef ALLOC
 #undef UPLOAD
+
+    // ---- group views: the env range of the shared buffers + the group's own settings and tables
+    {
+        int first = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            isx_handle::Group& grp = h->groups[(size_t)g];
+            const Dev& q = gd[(size_t)g];
+            Dev v = shard_of(d, first, q.E, g);
+            v.lanes = q.lanes; v.use_team = q.use_team; v.respawn = q.respawn; v.max_steps = q.max_steps;
+            v.traffic = q.traffic; v.T = q.T; v.auto_reset = q.auto_reset; v.rc = q.rc; v.seed = q.seed; v.env_base = q.env_base;
+            v.route_path = q.route_path; v.route_meta = q.route_meta; v.road_bits = q.road_bits; v.road_skip = q.road_skip;
+            v.box_lo = q.box_lo; v.box_hi = q.box_hi;
+            grp.d = v; grp.first = first;
+            first += q.E;
+        }
+        if (n_groups == 1) h->d.env_base = gd[0].env_base;
+    }
 
     // ---- contraction canary: the build must not fuse a*b+c (isx_math.cuh); fail loudly if it does
     {
@@ -284,36 +372,45 @@ int isx_create(const isx_config* cfg, isx_handle** out) {
     h->h_done = h->h_small + h->small_off[1]; h->h_status = h->h_small + h->small_off[2];
     h->h_term = h->h_small + h->small_off[3]; h->h_trunc = h->h_small + h->small_off[4];
     {
+        // Pipeline plan of the host-buffer step: env ranges whose kernels run while the copy engine drains the previous
+        // range's obs rows.  Measured on B200 + PCIe gen5 (tools/e2e_probe.py): the D2H of obs is 589 us of a 729 us step
+        // at 8192x8; each range costs ~55 us of fixed kernel latency, so few equal ranges beat many or geometric ones.
+        // One group: 4 equal ranges (ISX_PIPE_PLAN="w0,w1,..." (<= 8 weights) overrides, for tuning).  Several groups:
+        // every group is one range.
+        if (n_groups == 1) {
+            int w[8] = {1, 1, 1, 1, 0, 0, 0, 0}, nw = d.E >= 1024 ? 4 : 1;
+            if (const char* plan = getenv("ISX_PIPE_PLAN")) {
+                int k = 0;
+                for (const char* c = plan; *c && k < 8;) {
+                    char* endp = nullptr;
+                    const long v = std::strtol(c, &endp, 10);
+                    if (endp == c) break;
+                    if (v > 0) w[k++] = (int)v;
+                    c = (*endp == ',') ? endp + 1 : endp;
+                }
+                if (k > 0) nw = k;
+            }
+            long long tot = 0, acc = 0;
+            for (int i = 0; i < nw; ++i) tot += w[i];
+            for (int i = 0; i < nw; ++i) {
+                const int e0 = (int)((long long)d.E * acc / tot);
+                acc += w[i];
+                const int e1 = (int)((long long)d.E * acc / tot);
+                if (e1 > e0) h->pipe.push_back(isx_handle::Piece{0, e0, e1 - e0});
+            }
+        } else {
+            for (int g = 0; g < n_groups; ++g) h->pipe.push_back(isx_handle::Piece{g, 0, h->groups[(size_t)g].d.E});
+        }
+        h->ev_shard.resize(h->pipe.size(), nullptr);
+    }
+    {
         cudaError_t e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-        for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_shard[i], cudaEventDisableTiming);
+        for (size_t i = 0; i < h->ev_shard.size() && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_shard[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->pipe_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pipe_in, cudaEventDisableTiming);
         h->use_graph = getenv("ISX_NO_GRAPH") == nullptr;
         if (e != cudaSuccess) { isx_destroy(h); return fail(ISX_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
-    }
-    {
-        // Pipeline plan of the host-buffer step: env ranges whose kernels run while the copy engine drains the previous
-        // range's obs rows.  Measured on B200 + PCIe gen5 (tools/e2e_probe.py): the D2H of obs is 589 us of a 729 us step
-        // at 8192x8; each range costs ~55 us of fixed kernel latency, so few equal ranges beat many or geometric ones.
-        // ISX_PIPE_PLAN="w0,w1,..." (<= 8 weights) overrides, for tuning.
-        int w[8] = {1, 1, 1, 1, 0, 0, 0, 0}, nw = d.E >= 1024 ? 4 : 1;
-        if (const char* plan = getenv("ISX_PIPE_PLAN")) {
-            int k = 0;
-            for (const char* c = plan; *c && k < 8;) {
-                char* endp = nullptr;
-                const long v = std::strtol(c, &endp, 10);
-                if (endp == c) break;
-                if (v > 0) w[k++] = (int)v;
-                c = (*endp == ',') ? endp + 1 : endp;
-            }
-            if (k > 0) nw = k;
-        }
-        long long tot = 0, acc = 0;
-        for (int i = 0; i < nw; ++i) tot += w[i];
-        h->pipe_n = nw;
-        for (int i = 0; i < nw; ++i) { h->pipe_e0[i] = (int)((long long)d.E * acc / tot); acc += w[i]; }
-        h->pipe_e0[nw] = d.E;
     }
     *out = h;
     const int rc = isx_reset(h, nullptr, nullptr);
@@ -331,7 +428,7 @@ int isx_destroy(isx_handle* h) {
     if (h->pipe_stream) cudaStreamDestroy(h->pipe_stream);
     if (h->ev_pipe_in) cudaEventDestroy(h->ev_pipe_in);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    for (int i = 0; i < 8; ++i) if (h->ev_shard[i]) cudaEventDestroy(h->ev_shard[i]);
+    for (cudaEvent_t e : h->ev_shard) if (e) cudaEventDestroy(e);
     if (h->ev_copy_done) cudaEventDestroy(h->ev_copy_done);
     if (h->h_actions) cudaFreeHost(h->h_actions);
     if (h->h_obs) cudaFreeHost(h->h_obs);
@@ -341,35 +438,45 @@ int isx_destroy(isx_handle* h) {
 }
 
 int isx_num_envs(isx_handle* h) { return h ? h->d.E : fail(ISX_E_ARG, "null handle"); }
+int isx_num_groups(isx_handle* h) { return h ? (int)h->groups.size() : fail(ISX_E_ARG, "null handle"); }
+int isx_group_range(isx_handle* h, int32_t group, int32_t* first_env, int32_t* num_envs) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (group < 0 || group >= (int)h->groups.size()) return fail(ISX_E_ARG, "group %d out of range", group);
+    if (first_env) *first_env = h->groups[(size_t)group].first;
+    if (num_envs) *num_envs = h->groups[(size_t)group].d.E;
+    return ISX_OK;
+}
 int isx_num_agents(isx_handle* h) { return h ? h->d.N : fail(ISX_E_ARG, "null handle"); }
 
 int isx_reset(isx_handle* h, const uint8_t* env_mask_dev, void* stream) {
     if (!h) return fail(ISX_E_ARG, "null handle");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    CK(launch_reset(h->d, env_mask_dev, st));
-    CK(launch_lidar_obs(h->d, /*LIDAR_FROM_HITS*/ 1, h->lidar_grid, st));
+    for (const auto& g : h->groups) {
+        CK(launch_reset(g.d, env_mask_dev ? env_mask_dev + g.first : nullptr, st));
+        CK(launch_lidar_obs(g.d, /*LIDAR_FROM_HITS*/ 1, h->lidar_grid, st));
+    }
     return ISX_OK;
 }
 
 int isx_observe(isx_handle* h, void* stream) {
     if (!h) return fail(ISX_E_ARG, "null handle");
     CK(cudaSetDevice(h->device));
-    CK(launch_lidar_obs(h->d, 1, h->lidar_grid, static_cast<cudaStream_t>(stream)));
+    for (const auto& g : h->groups) CK(launch_lidar_obs(g.d, 1, h->lidar_grid, static_cast<cudaStream_t>(stream)));
     return ISX_OK;
 }
 
 // spawn_prob = 1 - exp(-density * dt) (TrafficFlow.cpp:321-322), evaluated on the host with the host libm's
 // expf — the same entry point the reference calls — once per distinct dt.
-static float spawn_prob_for(isx_handle* h, float dt) {
-    if (dt != h->last_dt) {
-        float dens = h->cfg.traffic_density;
+static float spawn_prob_for(isx_handle::Group& g, float dt) {
+    if (dt != g.last_dt) {
+        float dens = g.cfg.traffic_density;
         if (dens < 0.0f) dens = 0.0f;                       // configure_traffic clamps (IntersectionEnv.cpp:59)
         volatile float arg = -dens * dt;
-        h->last_prob = 1.0f - expf(arg);
-        h->last_dt = dt;
+        g.last_prob = 1.0f - expf(arg);
+        g.last_dt = dt;
     }
-    return h->last_prob;
+    return g.last_prob;
 }
 
 int isx_step(isx_handle* h, const float* actions_dev, float dt, void* stream) {
@@ -377,8 +484,10 @@ int isx_step(isx_handle* h, const float* actions_dev, float dt, void* stream) {
     if (!actions_dev) return fail(ISX_E_ARG, "actions_dev is null (use isx_rollout for on-device actions)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    CK(launch_dynamics(h->d, actions_dev, dt, spawn_prob_for(h, dt), st));
-    CK(launch_lidar_obs(h->d, 0, h->lidar_grid, st));
+    for (auto& g : h->groups) {
+        CK(launch_dynamics(g.d, actions_dev + (size_t)g.first * h->d.N * 2, dt, spawn_prob_for(g, dt), st));
+        CK(launch_lidar_obs(g.d, 0, h->lidar_grid, st));
+    }
     return ISX_OK;
 }
 
@@ -387,11 +496,11 @@ int isx_rollout(isx_handle* h, int32_t steps, float dt, void* stream) {
     if (steps < 0) return fail(ISX_E_ARG, "steps < 0");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    const float prob = spawn_prob_for(h, dt);
-    for (int s = 0; s < steps; ++s) {
-        CK(launch_dynamics(h->d, nullptr, dt, prob, st));
-        CK(launch_lidar_obs(h->d, 0, h->lidar_grid, st));
-    }
+    for (int s = 0; s < steps; ++s)
+        for (auto& g : h->groups) {
+            CK(launch_dynamics(g.d, nullptr, dt, spawn_prob_for(g, dt), st));
+            CK(launch_lidar_obs(g.d, 0, h->lidar_grid, st));
+        }
     return ISX_OK;
 }
 
@@ -411,19 +520,21 @@ int isx_rollout_timed4(isx_handle* h, int32_t steps, float dt, void* stream, flo
     if (steps < 1 || steps > 4096) return fail(ISX_E_ARG, "steps must be in [1,4096]");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    const float prob = spawn_prob_for(h, dt);
+    if (h->groups.size() != 1) return fail(ISX_E_STATE, "per-kernel timing is for single-group batches");
+    const Dev& gd0 = h->groups[0].d;
+    const float prob = spawn_prob_for(h->groups[0], dt);
     std::vector<cudaEvent_t> ev((size_t)steps * 5);
     for (auto& e : ev) CK(cudaEventCreate(&e));
     for (int s = 0; s < steps; ++s) {
         cudaEvent_t* e = &ev[(size_t)s * 5];
         CK(cudaEventRecord(e[0], st));
-        CK(launch_traffic(h->d, dt, prob, st));
+        CK(launch_traffic(gd0, dt, prob, st));
         CK(cudaEventRecord(e[1], st));
-        CK(launch_ego(h->d, nullptr, dt, st));
+        CK(launch_ego(gd0, nullptr, dt, st));
         CK(cudaEventRecord(e[2], st));
-        CK(launch_features(h->d, 0, st));
+        CK(launch_features(gd0, 0, st));
         CK(cudaEventRecord(e[3], st));
-        CK(launch_rays(h->d, 0, h->lidar_grid, st));
+        CK(launch_rays(gd0, 0, h->lidar_grid, st));
         CK(cudaEventRecord(e[4], st));
     }
     CK(cudaStreamSynchronize(st));
@@ -439,35 +550,17 @@ int isx_rollout_timed4(isx_handle* h, int32_t steps, float dt, void* stream, flo
     return ISX_OK;
 }
 
-// A view of envs [e0, e0+cnt) of the same buffers: every per-env array is contiguous per env, so a shard is the same
-// struct with advanced pointers; RNG stays keyed by the global env id through env_base.
-static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
-    Dev s = d;
-    const size_t oE = (size_t)e0, oEN = oE * d.N, oEM = oE * d.M, oEC = oE * (size_t)(d.N + d.M);
-    s.E = cnt; s.env_base = d.env_base + e0;
-    s.ex += oEN; s.ey += oEN; s.ev += oEN; s.eh += oEN; s.esteer += oEN; s.eacc += oEN; s.epd += oEN; s.epa0 += oEN; s.epa1 += oEN;
-    s.epidx += oEN; s.ealive += oEN;
-    s.nx += oEM; s.ny += oEM; s.nv += oEM; s.nh += oEM; s.nsteer += oEM; s.npidx += oEM; s.nroute += oEM; s.nuid += oEM;
-    s.ncount += oE; s.next_uid += oE; s.step_count += oE; s.tick += oE;
-    s.agent_rec = static_cast<char*>(d.agent_rec) + oEN * 16; s.car_rect = static_cast<char*>(d.car_rect) + oEC * 16;
-    s.cand += oEN * (size_t)(d.N + d.M); s.cand_n += oEN; s.ray_counter = d.ray_counter + shard_idx;
-    s.obs += oEN * ISX_OBS_DIM; s.reward += oEN; s.done += oEN; s.status += oEN;
-    s.terminated += oE; s.truncated += oE; s.agents_alive += oE; s.lidar_hit += oEN * ISX_MAX_RAYS;
-    s.events += oE; s.env_stats += oE * STAT_SLOTS;
-    return s;
-}
-
 // Enqueue one pipelined host-buffer step on `st` (+ the handle's copy stream, forked and joined through events).
 static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st) {
     const Dev& d = h->d;
     const size_t EN = (size_t)d.E * d.N;
-    const float prob = spawn_prob_for(h, dt);
     CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * EN * 2, cudaMemcpyHostToDevice, st));
-    for (int c = 0; c < h->pipe_n; ++c) {
-        const int e0 = h->pipe_e0[c], cnt = h->pipe_e0[c + 1] - e0;
-        if (cnt <= 0) continue;
-        const Dev sd = shard_of(d, e0, cnt, c);
-        const size_t aoff = (size_t)e0 * d.N, an = (size_t)cnt * d.N;
+    for (size_t c = 0; c < h->pipe.size(); ++c) {
+        const isx_handle::Piece& pc = h->pipe[c];
+        isx_handle::Group& grp = h->groups[(size_t)pc.group];
+        const float prob = spawn_prob_for(grp, dt);
+        const Dev sd = (pc.e0 == 0 && pc.cnt == grp.d.E) ? grp.d : shard_of(grp.d, pc.e0, pc.cnt, (int)c);
+        const size_t aoff = (size_t)(grp.first + pc.e0) * d.N, an = (size_t)pc.cnt * d.N;
         CK(launch_dynamics(sd, h->d_actions + aoff * 2, dt, prob, st));
         CK(launch_lidar_obs(sd, 0, h->lidar_grid, st));
         CK(cudaEventRecord(h->ev_shard[c], st));
@@ -566,8 +659,10 @@ int isx_get_buffers(isx_handle* h, isx_buffers* b) {
 int isx_get_env_state(isx_handle* h, int32_t env, isx_car_state* egos, isx_car_state* npcs, int32_t cap, int32_t* n_npcs,
                       int32_t* step_count, uint32_t* tick) {
     if (!h) return fail(ISX_E_ARG, "null handle");
-    const Dev& d = h->d;
-    if (env < 0 || env >= d.E) return fail(ISX_E_ARG, "env %d out of range", env);
+    if (env < 0 || env >= h->d.E) return fail(ISX_E_ARG, "env %d out of range", env);
+    const isx_handle::Group& grp = group_of(h, env);
+    const Dev& d = grp.d;                                 // the group's view; `env` becomes group-relative
+    env -= grp.first;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
     const size_t N = (size_t)d.N, M = (size_t)d.M, eo = (size_t)env * N, no = (size_t)env * M;
@@ -580,7 +675,7 @@ int isx_get_env_state(isx_handle* h, int32_t env, isx_car_state* egos, isx_car_s
         CK(pull(st, d.esteer, eo, N)); CK(pull(ac, d.eacc, eo, N)); CK(pull(pdv, d.epd, eo, N)); CK(pull(a0, d.epa0, eo, N));
         CK(pull(a1, d.epa1, eo, N)); CK(pull(pi, d.epidx, eo, N)); CK(pull(al, d.ealive, eo, N));
         for (size_t i = 0; i < N; ++i)
-            egos[i] = isx_car_state{x[i], y[i], v[i], hd[i], ac[i], st[i], pdv[i], a0[i], a1[i], pi[i], (int32_t)i, al[i] ? 1 : 0, 0u, h->routes[i].intent};
+            egos[i] = isx_car_state{x[i], y[i], v[i], hd[i], ac[i], st[i], pdv[i], a0[i], a1[i], pi[i], (int32_t)i, al[i] ? 1 : 0, 0u, grp.routes[i].intent};
     }
     int cnt = 0;
     if (d.traffic) CK(cudaMemcpy(&cnt, d.ncount + env, sizeof(int), cudaMemcpyDeviceToHost));
@@ -590,7 +685,7 @@ int isx_get_env_state(isx_handle* h, int32_t env, isx_car_state* egos, isx_car_s
         CK(pull(st, d.nsteer, no, M)); CK(pull(pi, d.npidx, no, M)); CK(pull(rt, d.nroute, no, M)); CK(pull(uid, d.nuid, no, M));
         for (int i = 0; i < cnt && i < cap; ++i) {
             const size_t k = (size_t)i;
-            npcs[i] = isx_car_state{x[k], y[k], v[k], hd[k], 0.0f, st[k], 0.0f, 0.0f, 0.0f, pi[k], rt[k], 1, uid[k], h->routes[N + (size_t)rt[k]].intent};
+            npcs[i] = isx_car_state{x[k], y[k], v[k], hd[k], 0.0f, st[k], 0.0f, 0.0f, 0.0f, pi[k], rt[k], 1, uid[k], grp.routes[N + (size_t)rt[k]].intent};
         }
     }
     if (step_count) CK(cudaMemcpy(step_count, d.step_count + env, sizeof(int), cudaMemcpyDeviceToHost));
@@ -601,8 +696,10 @@ int isx_get_env_state(isx_handle* h, int32_t env, isx_car_state* egos, isx_car_s
 int isx_set_env_state(isx_handle* h, int32_t env, const isx_car_state* egos, const isx_car_state* npcs, int32_t n_npcs,
                       int32_t step_count, uint32_t tick) {
     if (!h) return fail(ISX_E_ARG, "null handle");
-    const Dev& d = h->d;
-    if (env < 0 || env >= d.E) return fail(ISX_E_ARG, "env %d out of range", env);
+    if (env < 0 || env >= h->d.E) return fail(ISX_E_ARG, "env %d out of range", env);
+    const isx_handle::Group& grp = group_of(h, env);
+    const Dev& d = grp.d;
+    env -= grp.first;
     if (n_npcs < 0 || n_npcs > d.M || (n_npcs > 0 && !d.traffic)) return fail(ISX_E_ARG, "n_npcs %d exceeds capacity %d", n_npcs, d.traffic ? d.M : 0);
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());

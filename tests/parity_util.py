@@ -38,6 +38,22 @@ def make_pair(benv_cls, cfg, checker=None, seed=0, env_id_base=0):
     return b, refs
 
 
+def make_group_pair(benv_cls, cfgs, checker=None):
+    """Heterogeneous batch (list of config dicts, each with its own seed / env_id_base) and one checker env per env,
+    configured like the group the env belongs to."""
+    checker = checker or checker_class()
+    b = benv_cls([dict(c) for c in cfgs])
+    refs = []
+    for cfg, gc in zip(cfgs, b.group_configs):
+        for e in range(gc["num_envs"]):
+            refs.append(checker(num_lanes=gc["num_lanes"], ego_routes=gc["ego_routes"], use_team=bool(cfg.get("use_team_reward", False)),
+                                respawn=bool(cfg.get("respawn_enabled", True)), max_steps=int(cfg.get("max_steps", 2000)),
+                                traffic=bool(cfg.get("traffic_flow", False)), density=float(cfg.get("traffic_density", 0.5)),
+                                traffic_routes=gc["traffic_routes"], reward=tuple(_reward_vec(cfg)), lidar_rays=gc["lidar_rays"],
+                                seed=int(cfg.get("seed", 0)), env_id=int(cfg.get("env_id_base", 0)) + e))
+    return b, refs
+
+
 def _reward_vec(cfg):
     from marl_traffic_intersection_b200.utils import reward_vector
     return reward_vector(cfg.get("reward_config"))

@@ -316,3 +316,73 @@ def test_equal_distance_neighbours_follow_std_sort(n, cap, density):
     free_run(b, refs, steps=200, seed=53)
     assert b.stats()["neighbor_tie_sorts"] > 0
     b.close()
+
+
+HETERO = [
+    dict(num_envs=3, num_agents=4, num_lanes=2, ego_routes=R2[:4], traffic_flow=True, traffic_density=3.0, seed=61, env_id_base=100, max_steps=150),
+    dict(num_envs=2, num_agents=4, num_lanes=3, ego_routes=R3[:4], use_team_reward=True, seed=62, env_id_base=7, respawn_enabled=False, max_steps=90),
+    dict(num_envs=4, num_agents=4, num_lanes=3, ego_routes=R3[4:8], traffic_flow=True, traffic_density=6.0, seed=63, env_id_base=0,
+         reward_config=dict(progress_scale=2.0, crash_vehicle_penalty=-4.0, success_reward=30.0, team_alpha=0.5), use_team_reward=True),
+    dict(num_envs=1, num_agents=4, num_lanes=4, ego_routes=[("IN_1", "OUT_9"), ("IN_6", "OUT_15"), ("IN_11", "OUT_2"), ("IN_16", "OUT_4")],
+         traffic_flow=True, traffic_density=0.5, traffic_routes=[("IN_2", "OUT_10"), ("IN_7", "OUT_13")], seed=64, env_id_base=5),
+]
+
+
+def test_heterogeneous_batch_matches_per_env_checkers():
+    """lanes / routes / traffic density / reward weights / episode settings differ per group inside ONE
+    batch; every env must still match a checker env configured like its group — device step and host-buffer step."""
+    from parity_util import make_group_pair
+    for host_api in (False, True):
+        b, refs = make_group_pair(_benv(), HETERO)
+        assert b.group_ranges == [(0, 3), (3, 2), (5, 4), (9, 1)] and b.num_envs == 10
+
+        def pol(obs, t):
+            rng = np.random.default_rng(1000 + t)
+            return rng.uniform(-1, 1, (10, 4, 2)).astype(np.float32)
+        free_run(b, refs, steps=220, seed=0, policy=pol, host_api=host_api)
+        b.close()
+
+
+def test_heterogeneous_group_equals_standalone_batch():
+    """Each group keeps its own seed / env_id_base, so after an on-device rollout (Philox actions, auto-reset) its slice of
+    the heterogeneous batch is bit-identical to a stand-alone batch created from the same config; snapshots and
+    per-env state access address envs by their position in the whole batch."""
+    import torch
+    cfgs = [dict(c, auto_reset=True, max_steps=60) for c in HETERO]
+    het = _benv()(cfgs)
+    solo = [_benv()(c) for c in cfgs]
+    snap = het.snapshot()
+    het.rollout(150)
+    for s in solo:
+        s.rollout(150)
+    torch.cuda.synchronize()
+    for (first, cnt), s in zip(het.group_ranges, solo):
+        for k in ("obs", "reward", "status", "ego_x", "ego_heading", "npc_count", "tick", "step", "lidar_hit", "events"):
+            a, c = het.buf[k][first:first + cnt].cpu().numpy(), s.buf[k].cpu().numpy()
+            assert (a.view(np.uint8) == c.view(np.uint8)).all(), k
+        n = int(s.buf["npc_count"].max())
+        if n:
+            assert (het.buf["npc_x"][first:first + cnt, :n].cpu().numpy().view(np.uint32) == s.buf["npc_x"][:, :n].cpu().numpy().view(np.uint32)).all()
+    # per-env state access resolves the group (env 9 = the 4-lane group: intents come from ITS routes)
+    egos, npcs, n_npc, sc, tk = het.get_env_state(9)
+    e2, _, _, sc2, tk2 = solo[3].get_env_state(0)
+    assert [c.intention for c in egos] == [c.intention for c in e2] and sc == sc2 and tk == tk2
+    # masked restore across group boundaries: envs 2..6 go back to the reset state, the others keep going
+    mask = torch.zeros(10, dtype=torch.uint8, device="cuda"); mask[2:7] = 1
+    keep = het.buf["ego_x"].clone()
+    het.restore(snap, mask)
+    torch.cuda.synchronize()
+    assert (het.buf["tick"][2:7] == 0).all() and (het.buf["ego_x"][:2] == keep[:2]).all() and (het.buf["ego_x"][7:] == keep[7:]).all()
+    het.rollout(50)
+    st = het.stats()
+    assert st["agent_steps"] == 10 * 4 * 200
+    het.close()
+    for s in solo:
+        s.close()
+
+
+def test_heterogeneous_batch_rejects_shape_mismatch():
+    with pytest.raises(Exception):
+        _benv()([dict(num_envs=2, num_agents=2, ego_routes=R3[:2]), dict(num_envs=2, num_agents=3, ego_routes=R3[:3])])
+    with pytest.raises(Exception):
+        _benv()([dict(num_envs=2, num_agents=2, ego_routes=R3[:2], lidar_rays=72), dict(num_envs=2, num_agents=2, ego_routes=R3[:2], lidar_rays=96)])
