@@ -199,6 +199,12 @@ int isx_snapshot_destroy(isx_snapshot *s);
 /* get_observations() (IntersectionEnv.cpp:418-520) for the current state, without stepping. */
 int isx_observe(isx_handle *h, void *stream);
 
+/* Headless debug picture of one env (stands in for the Windows-only window of
+ * Renderer.cpp:520-646): rgb_dev = DEVICE uint8 [750][750][3].  Road / grass / centre lines from the tables the
+ * simulation itself uses, alive egos in a six-colour palette with a head marker, NPCs grey, and the lidar beams that
+ * hit something (green) with their exact hit pixel (red), as draw_lidar does.  Stream-ordered. */
+int isx_render(isx_handle *h, int32_t env, uint8_t *rgb_dev, void *stream);
+
 int isx_stats_read(isx_handle *h, isx_stats *out);     /* synchronous */
 int isx_stats_reset(isx_handle *h);
 /* Tuning aid: with ISX_TRACE=1 in the environment at isx_create, k_traffic stamps clock64() at its phase boundaries

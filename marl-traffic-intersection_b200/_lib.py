@@ -72,7 +72,7 @@ EXPORTS = [
     "isx_last_error", "isx_abi_version", "isx_create", "isx_create_groups", "isx_num_groups", "isx_group_range", "isx_destroy", "isx_reset", "isx_step", "isx_step_host",
     "isx_step_pinned", "isx_host_views",
     "isx_rollout", "isx_rollout_timed", "isx_rollout_timed4", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
-    "isx_observe", "isx_snapshot_create", "isx_snapshot_save", "isx_snapshot_restore", "isx_snapshot_destroy",
+    "isx_observe", "isx_render", "isx_snapshot_create", "isx_snapshot_save", "isx_snapshot_restore", "isx_snapshot_destroy",
     "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_stats_device_ptr", "isx_route", "isx_math_probe",
 ]
 
@@ -114,6 +114,7 @@ def load_library(path: str | None = None):
     lib.isx_get_env_state.argtypes = [vp, i32, C.POINTER(CarState), C.POINTER(CarState), i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_uint32)]
     lib.isx_set_env_state.argtypes = [vp, i32, C.POINTER(CarState), C.POINTER(CarState), i32, i32, C.c_uint32]
     lib.isx_observe.argtypes = [vp, vp]
+    lib.isx_render.argtypes = [vp, i32, vp, vp]
     lib.isx_snapshot_create.argtypes = [vp, C.POINTER(vp)]
     lib.isx_snapshot_save.argtypes = [vp, vp, vp]
     lib.isx_snapshot_restore.argtypes = [vp, vp, vp, vp]

@@ -228,6 +228,12 @@ class BatchedIntersectionEnv:
         _lib.check(self._lib, self._lib.isx_observe(self._h, self._stream()))
         return self.buf["obs"]
 
+    def render(self, env: int = 0) -> torch.Tensor:
+        """Headless debug picture of one env: uint8 cuda tensor [750, 750, 3] (road, cars, the lidar beams that hit)."""
+        img = torch.empty((750, 750, 3), dtype=torch.uint8, device=self.device)
+        _lib.check(self._lib, self._lib.isx_render(self._h, int(env), C.c_void_p(img.data_ptr()), self._stream()))
+        return img
+
     # ------------------------------------------------------------------ snapshots (get_state / set_state for the batch)
     def snapshot(self):
         """Save the full state of every env on the device (EnvState of the reference, for MCTS-style rollbacks)."""

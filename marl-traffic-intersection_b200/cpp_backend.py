@@ -169,7 +169,11 @@ class IntersectionEnv:
         return r
 
     def render(self, show_lane_ids=False, show_lidar=False):
-        return None                                   # the Windows/GLFW renderer is out of scope
+        """No window (the reference's is Windows/GLFW); returns the headless picture instead:
+        uint8 ndarray [750, 750, 3] from isx_render, or None before the first reset."""
+        if self._benv is None:
+            return None
+        return self._benv.render(0).cpu().numpy()
 
     def window_should_close(self):
         return True

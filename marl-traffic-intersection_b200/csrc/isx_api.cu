@@ -26,6 +26,7 @@ cudaError_t launch_rays(const Dev& d, int mode, int grid_cap, cudaStream_t st);
 cudaError_t launch_reset(const Dev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t launch_reduce_stats(const Dev& d, cudaStream_t st);
 cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st);
+cudaError_t launch_render(const Dev& d, int env, uint8_t* rgb, cudaStream_t st);
 cudaError_t launch_snapshot_restore(const void* tab, int n_arrays, const uint8_t* mask, int E, cudaStream_t st);
 cudaError_t launch_math_probe(int n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr, cudaStream_t st);
 cudaError_t lidar_set_smem_attr(const Dev& d);
@@ -639,6 +640,15 @@ int isx_step_host(isx_handle* h, const float* actions, float dt, float* obs, flo
     if (status) std::memcpy(status, h->h_status, EN);
     if (terminated) std::memcpy(terminated, h->h_term, E);
     if (truncated) std::memcpy(truncated, h->h_trunc, E);
+    return ISX_OK;
+}
+
+int isx_render(isx_handle* h, int32_t env, uint8_t* rgb_dev, void* stream) {
+    if (!h || !rgb_dev) return fail(ISX_E_ARG, "null argument");
+    if (env < 0 || env >= h->d.E) return fail(ISX_E_ARG, "env %d out of range", env);
+    const isx_handle::Group& grp = group_of(h, env);
+    CK(cudaSetDevice(h->device));
+    CK(launch_render(grp.d, env - grp.first, rgb_dev, static_cast<cudaStream_t>(stream)));
     return ISX_OK;
 }
 

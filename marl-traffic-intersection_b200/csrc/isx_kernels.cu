@@ -725,6 +725,117 @@ k_lidar_obs(const Dev d, int mode) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k_render
+// Headless debug picture of ONE env (stands in for the Windows-only window of Renderer.cpp:520-646):
+// thread per pixel of a 750x750 RGB image.  Road surface / grass come from the same folded bitmap the beams march,
+// centre-line pixels from is_line_px, egos (alive ones) in a six-colour palette with a dark head marker, NPCs grey,
+// and — as draw_lidar does — only the beams that hit something: a green segment with a red end point.  The CTA first
+// stages car frames and beam end points (exact hit pixel: ray_pixel of sample k) in shared memory.
+struct RenderCar { float x, y, c, s; uint32_t rgb; int npc; };
+struct RenderBeam { short x0, y0, x1, y1; };
+constexpr int RENDER_MAX_CARS = ISX_MAX_AGENTS + ISX_MAX_NPC;
+constexpr int RENDER_MAX_BEAMS = 1024;     // per staging round
+
+__device__ __forceinline__ uint32_t rgb_pack(int r, int g, int b) { return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16); }
+
+__global__ void __launch_bounds__(256)
+k_render(const Dev d, int env, uint8_t* __restrict__ rgb) {
+    __shared__ RenderCar s_car[RENDER_MAX_CARS];
+    __shared__ RenderBeam s_beam[RENDER_MAX_BEAMS];
+    __shared__ int s_ncar, s_nbeam;
+    const int tid = threadIdx.x;
+    const int pix = blockIdx.x * blockDim.x + tid;
+    const int x = pix % WIDTH, y = pix / WIDTH;
+    const bool inside = pix < WIDTH * HEIGHT;
+    const int N = d.N, R = d.R;
+    const int nn = d.traffic ? d.ncount[env] : 0;
+    if (tid == 0) { s_ncar = 0; s_nbeam = 0; }
+    __syncthreads();
+    for (int k = tid; k < N + nn; k += blockDim.x) {
+        RenderCar c;
+        bool draw = true;
+        if (k < N) {
+            const int j = env * N + k;
+            draw = d.ealive[j] != 0;
+            const uint32_t pal[6] = {rgb_pack(231, 76, 60), rgb_pack(52, 152, 219), rgb_pack(46, 204, 113),
+                                     rgb_pack(155, 89, 182), rgb_pack(241, 196, 15), rgb_pack(230, 126, 34)};
+            float sn, cs;
+            sincosf_(d.eh[j], &sn, &cs);
+            c = RenderCar{d.ex[j], d.ey[j], cs, sn, pal[k % 6], 0};
+        } else {
+            const int j = env * d.M + (k - N);
+            float sn, cs;
+            sincosf_(d.nh[j], &sn, &cs);
+            c = RenderCar{d.nx[j], d.ny[j], cs, sn, rgb_pack(128, 128, 128), 1};
+        }
+        if (!draw) c.npc = -1;
+        s_car[k] = c;                              // list order = paint order (egos, then NPCs), as draw_cars
+    }
+    if (tid == 0) s_ncar = N + nn;
+    // base colour
+    uint32_t col = 0;
+    if (inside) {
+        int u = x - ROAD_HALF; u = u < 0 ? -u : u;
+        int v = y - ROAD_HALF; v = v < 0 ? -v : v;
+        const bool road = (d.road_bits[v * ROAD_WORDS + (u >> 5)] >> (u & 31)) & 1u;
+        col = road ? rgb_pack(70, 70, 74) : rgb_pack(58, 125, 68);
+        if (road && is_line_px(d.lanes, x, y)) col = rgb_pack(240, 200, 40);
+    }
+    // beams that hit, RENDER_MAX_BEAMS at a time
+    const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;
+    bool on_beam = false, on_tip = false;
+    for (int base = 0; base < N * R; base += RENDER_MAX_BEAMS) {
+        __syncthreads();
+        if (tid == 0) s_nbeam = 0;
+        __syncthreads();
+        for (int b = base + tid; b < N * R && b < base + RENDER_MAX_BEAMS; b += blockDim.x) {
+            const int a = b / R, i = b - a * R;
+            const int j = env * N + a;
+            const int k = d.ealive[j] ? d.lidar_hit[(size_t)j * ISX_MAX_RAYS + i] : 0;
+            if (k) {
+                float sn, cs;
+                sincosf_(d.eh[j] + d.rel_angle[i], &sn, &cs);
+                int px, py;
+                ray_pixel(d.ex[j], d.ey[j], cs, -sn, k, px, py);
+                s_beam[atomicAdd(&s_nbeam, 1)] = RenderBeam{(short)f2i_rz(d.ex[j]), (short)f2i_rz(d.ey[j]), (short)px, (short)py};
+            }
+        }
+        __syncthreads();
+        const int nb = s_nbeam;
+        for (int b = 0; b < nb && inside; ++b) {
+            const RenderBeam q = s_beam[b];
+            const float ax = (float)q.x0 + 0.5f, ay = (float)q.y0 + 0.5f, bx = (float)q.x1 + 0.5f, by = (float)q.y1 + 0.5f;
+            const float ex = fx - bx, ey = fy - by;
+            if (ex * ex + ey * ey <= 2.5f * 2.5f) on_tip = true;
+            const float vx = bx - ax, vy = by - ay, wx = fx - ax, wy = fy - ay;
+            const float len2 = vx * vx + vy * vy;
+            float t = len2 > 0.0f ? (wx * vx + wy * vy) / len2 : 0.0f;
+            t = fminf(fmaxf(t, 0.0f), 1.0f);
+            const float qx = wx - t * vx, qy = wy - t * vy;
+            if (qx * qx + qy * qy <= 0.75f * 0.75f) on_beam = true;
+        }
+    }
+    __syncthreads();
+    if (!inside) return;
+    if (on_beam) col = rgb_pack(60, 220, 90);
+    // cars on top of the beams, end points on top of everything (later cars overwrite earlier ones, like the painter)
+    const float hl = CAR_LENGTH * 0.5f, hw = CAR_WIDTH * 0.5f;
+    for (int k = 0; k < s_ncar; ++k) {
+        const RenderCar c = s_car[k];
+        if (c.npc < 0) continue;
+        const float dx = fx - c.x, dy = fy - c.y;
+        const float lx = dx * c.c - dy * c.s, ly = dx * c.s + dy * c.c;      // screen -> car frame (screen y points down)
+        if (fabsf(lx) <= hl && fabsf(ly) <= hw) {
+            col = c.rgb;
+            if (lx >= -hl + 0.70f * CAR_LENGTH && lx <= -hl + 0.95f * CAR_LENGTH && fabsf(ly) <= hw - 2.0f)
+                col = c.npc ? rgb_pack(20, 20, 20) : rgb_pack(250, 250, 250);
+        }
+    }
+    if (on_tip) col = rgb_pack(220, 30, 30);
+    uint8_t* o = rgb + (size_t)pix * 3;
+    o[0] = (uint8_t)(col & 255u); o[1] = (uint8_t)((col >> 8) & 255u); o[2] = (uint8_t)((col >> 16) & 255u);
+}
+
 // ------------------------------------------------------------------------------------------------ small kernels
 // reset() + add_car_with_route (IntersectionEnv.cpp:66-131) for masked envs
 __global__ void k_reset(const Dev d, const uint8_t* __restrict__ mask) {
@@ -862,6 +973,10 @@ cudaError_t launch_reduce_stats(const Dev& d, cudaStream_t st) {
 cudaError_t launch_snapshot_restore(const void* tab, int n_arrays, const uint8_t* mask, int E, cudaStream_t st) {
     const long long n = (long long)E * n_arrays;
     k_snapshot_restore<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const SnapArray*>(tab), n_arrays, mask, E);
+    return cudaGetLastError();
+}
+cudaError_t launch_render(const Dev& d, int env, uint8_t* rgb, cudaStream_t st) {
+    k_render<<<(WIDTH * HEIGHT + 255) / 256, 256, 0, st>>>(d, env, rgb);
     return cudaGetLastError();
 }
 cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st) {

@@ -111,7 +111,7 @@ class IntersectionEnv:
         return obs, rewards, terminated, truncated, info
 
     def render(self, show_lane_ids: bool | None = None, show_lidar: bool | None = None):
-        return None   # headless only; the reference renderer is Windows/GLFW (out of scope)
+        return self.env.render()   # headless: an rgb array instead of the reference's Windows/GLFW window
 
     def close(self):
         if getattr(self.env, "_benv", None) is not None:

@@ -65,3 +65,50 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         BatchedIntersectionEnv({"num_envs": 2, "num_agents": 2, "ego_routes": [("IN_6", "OUT_2")]})
     assert cpp_backend.has_cpp_backend()
+
+
+R3 = po.ROUTES_3LANES
+
+
+def _benv():
+    from marl_traffic_intersection_b200 import BatchedIntersectionEnv
+    return BatchedIntersectionEnv
+
+
+def test_headless_render_shows_road_cars_and_hits():
+    """isx_render: pixel classes at known places — road/grass exactly as the checker's road map away
+    from cars and beams, every alive ego's centre in its palette colour, every lidar hit pixel red."""
+    import torch
+    cfg = dict(num_envs=3, num_agents=4, num_lanes=3, ego_routes=R3[:4], traffic_flow=True, traffic_density=4.0, seed=71, auto_reset=True)
+    b = _benv()(cfg)
+    b.rollout(140)
+    img = b.render(1).cpu().numpy()
+    assert img.shape == (750, 750, 3) and img.dtype == np.uint8
+    road = po.ref_unit().road_map(3) if po.have_ref() else po.oracle_unit().road_map(3)
+    road = np.asarray(road).reshape(750, 750).astype(bool)
+    grass, surf = np.array([58, 125, 68]), np.array([70, 70, 74])
+    is_grass, is_surf = (img == grass).all(-1), (img == surf).all(-1)
+    assert not (is_grass & road).any() and not (is_surf & ~road).any()          # never the wrong base colour
+    assert is_grass[~road].mean() > 0.95 and is_surf[road].mean() > 0.6
+    pal = np.array([[231, 76, 60], [52, 152, 219], [46, 204, 113], [155, 89, 182]])
+    ex, ey, al = (b.buf[k][1].cpu().numpy() for k in ("ego_x", "ego_y", "ego_alive"))
+    hits = b.buf["lidar_hit"][1].cpu().numpy()
+    seen_hit = 0
+    for a in range(4):
+        if not al[a]:
+            continue
+        cx, cy = int(ex[a]), int(ey[a])
+        if 0 <= cx < 750 and 0 <= cy < 750:
+            px = img[cy, cx]
+            assert (px == pal[a]).all() or (px == [220, 30, 30]).all() or any((px == pal[o]).all() for o in range(4)) or (px == [128, 128, 128]).all() or (px == [20, 20, 20]).all() or (px == [250, 250, 250]).all(), (a, px)
+        seen_hit += int((hits[a][:96] > 0).sum())
+    assert seen_hit > 0 and ((img == [220, 30, 30]).all(-1)).sum() >= 5
+    # the single-env facade returns the same kind of picture
+    from marl_traffic_intersection_b200 import IntersectionEnv
+    env = IntersectionEnv({"num_agents": 2, "ego_routes": R3[:2]})
+    assert env.render() is None or env.render().shape == (750, 750, 3)
+    env.reset()
+    pic = env.render()
+    assert pic.shape == (750, 750, 3) and (pic[int(env.env.cars[0].state.y), int(env.env.cars[0].state.x)] == [231, 76, 60]).all()
+    env.close()
+    b.close()
