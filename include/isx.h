@@ -210,6 +210,9 @@ int isx_stats_reset(isx_handle *h);
 /* Tuning aid: with ISX_TRACE=1 in the environment at isx_create, k_traffic stamps clock64() at its phase boundaries
  * per env; this copies the [E][16] stamps out (slots 0..5 = phase boundaries, 6 = NPC count).  ISX_E_STATE when off. */
 int isx_trace_read(isx_handle *h, long long *out16_per_env);
+/* Tuning aid: one host-buffer step (stream path) with CUDA events around every pipeline range; ms[4*i+0..3] = kernels
+ * begin / kernels end / copy begin / copy end of range i, ms since the step began.  Returns the number of ranges. */
+int isx_pipe_timeline(isx_handle *h, float dt, void *stream, float *ms, int32_t cap_ranges);
 /* device pointer to the raw counters (int64[16], reward_sum as double in slot 15) for an NCCL all-reduce */
 int isx_stats_device_ptr(isx_handle *h, void **ptr, int32_t *n_int64);
 

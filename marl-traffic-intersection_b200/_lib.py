@@ -73,7 +73,7 @@ EXPORTS = [
     "isx_step_pinned", "isx_host_views",
     "isx_rollout", "isx_rollout_timed", "isx_rollout_timed4", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
     "isx_observe", "isx_render", "isx_snapshot_create", "isx_snapshot_save", "isx_snapshot_restore", "isx_snapshot_destroy",
-    "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_stats_device_ptr", "isx_route", "isx_math_probe",
+    "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_pipe_timeline", "isx_stats_device_ptr", "isx_route", "isx_math_probe",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load_library(path: str | None = None):
     lib.isx_stats_read.argtypes = [vp, C.POINTER(Stats)]
     lib.isx_stats_reset.argtypes = [vp]
     lib.isx_trace_read.argtypes = [vp, vp]
+    lib.isx_pipe_timeline.argtypes = [vp, f32, vp, C.POINTER(f32), i32]
     lib.isx_stats_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
     lib.isx_route.argtypes = [i32, C.c_char_p, C.c_char_p, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]
     lib.isx_math_probe.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]

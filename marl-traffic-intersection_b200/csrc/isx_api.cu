@@ -552,8 +552,9 @@ int isx_rollout_timed4(isx_handle* h, int32_t steps, float dt, void* stream, flo
 }
 
 // Enqueue one pipelined host-buffer step on `st` (+ the handle's copy stream, forked and joined through events).
-static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st) {
+static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::vector<cudaEvent_t>* tl = nullptr) {
     const Dev& d = h->d;
+    if (tl) CK(cudaEventRecord((*tl)[0], st));
     const size_t EN = (size_t)d.E * d.N;
     CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * EN * 2, cudaMemcpyHostToDevice, st));
     for (size_t c = 0; c < h->pipe.size(); ++c) {
@@ -562,11 +563,15 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st) {
         const float prob = spawn_prob_for(grp, dt);
         const Dev sd = (pc.e0 == 0 && pc.cnt == grp.d.E) ? grp.d : shard_of(grp.d, pc.e0, pc.cnt, (int)c);
         const size_t aoff = (size_t)(grp.first + pc.e0) * d.N, an = (size_t)pc.cnt * d.N;
+        if (tl) CK(cudaEventRecord((*tl)[1 + 4 * c], st));
         CK(launch_dynamics(sd, h->d_actions + aoff * 2, dt, prob, st));
         CK(launch_lidar_obs(sd, 0, h->lidar_grid, st));
+        if (tl) CK(cudaEventRecord((*tl)[2 + 4 * c], st));
         CK(cudaEventRecord(h->ev_shard[c], st));
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_shard[c], 0));
+        if (tl) CK(cudaEventRecord((*tl)[3 + 4 * c], h->copy_stream));
         CK(cudaMemcpyAsync(h->h_obs + aoff * ISX_OBS_DIM, d.obs + aoff * ISX_OBS_DIM, sizeof(float) * an * ISX_OBS_DIM, cudaMemcpyDeviceToHost, h->copy_stream));
+        if (tl) CK(cudaEventRecord((*tl)[4 + 4 * c], h->copy_stream));
     }
     // the stream order of copy_stream puts this after the last shard's kernels (its wait on ev_shard[last])
     CK(cudaMemcpyAsync(h->h_small, h->d_small, h->small_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
@@ -610,6 +615,26 @@ int isx_step_pinned(isx_handle* h, float dt, void* stream) {
     CK(cudaGraphLaunch(h->pipe_exec, h->pipe_stream));
     CK(cudaStreamSynchronize(h->pipe_stream));
     return ISX_OK;
+}
+
+// Tuning aid: ONE host-buffer step on the plain stream path with timing events around every range's kernels and copy.
+// ms[4*i + 0..3] = kernels begin, kernels end, copy begin, copy end of range i, in ms since the step's first operation.
+// Returns the number of ranges (or an error).  The step itself is a normal step (results in the pinned views).
+int isx_pipe_timeline(isx_handle* h, float dt, void* stream, float* ms, int32_t cap_ranges) {
+    if (!h || !ms) return fail(ISX_E_ARG, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const size_t n = h->pipe.size();
+    if ((size_t)cap_ranges < n) return fail(ISX_E_ARG, "need room for %d ranges", (int)n);
+    std::vector<cudaEvent_t> ev(1 + 4 * n);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    const int rc = enqueue_pinned_step(h, dt, st, &ev);
+    if (rc) return rc;
+    CK(cudaEventSynchronize(h->ev_copy_done));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    for (size_t i = 0; i < 4 * n; ++i) CK(cudaEventElapsedTime(&ms[i], ev[0], ev[1 + i]));
+    for (auto& e : ev) cudaEventDestroy(e);
+    return (int)n;
 }
 
 int isx_host_views(isx_handle* h, float** actions, float** obs, float** reward, uint8_t** done, uint8_t** status,

@@ -94,8 +94,18 @@ struct NpcSmem {
 // order, NPC-NPC SAT, ordered erase.  The lanes spread over path-window points / other NPCs / ghost-path points.
 // Reads the egos' PRE-step positions (spawn blocking, :244-249), so it runs before k_ego.  Only launched when traffic
 // flow is enabled.
+// Programmatic dependent launch (sm_90+): the four step kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of kernel k+1 may become resident while kernel k drains
+// its last wave.  Every kernel first lets ITS successor start (launch_dependents), runs whatever does not depend on the
+// predecessor (k_lidar_obs: staging 27 KB of constant tables per CTA), and only then waits for the predecessor grid to
+// complete and flush (wait) — nothing a predecessor writes is touched before that.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __global__ void __launch_bounds__(DYN_WARPS * 32, ISX_TRAFFIC_MINB)
 k_traffic(const Dev d, float dt, float spawn_prob) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ NpcSmem sm_all[DYN_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * DYN_WARPS + warp;
@@ -289,6 +299,8 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
 template <int NP>
 __global__ void __launch_bounds__(EGO_THREADS, ISX_EGO_MINB)
 k_ego(const Dev d, const float* __restrict__ actions, float dt) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int EPW = 32 / NP;                                  // envs per warp
     constexpr unsigned LOW = NP == 32 ? 0xffffffffu : ((1u << NP) - 1u);
     const int lane = threadIdx.x & 31;
@@ -473,6 +485,8 @@ __global__ void __launch_bounds__(FEAT_THREADS, ISX_FEAT_MINB)
 k_features(const Dev d, int mode) {
     // FOUR lanes per ego (a "quad"): sub-lane q handles the cars q, q+4, ... of the env, so the dependent chain per
     // thread is a quarter as long and there are 4x more warps in flight (thread-per-ego ran at 20% occupancy).
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, q = lane & 3, qshift = lane & ~3;
     const int N = d.N, R = d.R;
@@ -654,7 +668,8 @@ k_lidar_obs(const Dev d, int mode) {
     float* s_rel = reinterpret_cast<float*>(smem_raw + ROAD_BITS_BYTES + ROAD_SKIP_BYTES);
     const int tid = threadIdx.x, lane = tid & 31;
     const int R = RT ? RT : d.R;
-    {   // 16-byte copies; the global tables are padded to ROAD_*_BYTES
+    pdl_launch_dependents();
+    {   // 16-byte copies; the global tables are padded to ROAD_*_BYTES (constant since isx_create: safe before pdl_wait)
         const uint4* gb = reinterpret_cast<const uint4*>(d.road_bits);
         const uint4* gs = reinterpret_cast<const uint4*>(d.road_skip);
         uint4* sb = reinterpret_cast<uint4*>(s_bits);
@@ -663,6 +678,7 @@ k_lidar_obs(const Dev d, int mode) {
         for (int i = tid; i < ROAD_SKIP_BYTES / 16; i += LID_THREADS) ss[i] = gs[i];
         for (int i = tid; i < R; i += LID_THREADS) s_rel[i] = d.rel_angle[i];
     }
+    pdl_wait();                                      // k_features' records, candidate lists and the zeroed work counter
     __syncthreads();
     const RoadView road{s_bits, s_skip, d.box_lo, d.box_hi};
     const int CE = d.N + d.M;
@@ -916,25 +932,40 @@ size_t lidar_smem_bytes(const Dev& d) { (void)d; return (size_t)ROAD_BITS_BYTES 
 size_t road_bits_bytes() { return ROAD_BITS_BYTES; }
 size_t road_skip_bytes() { return ROAD_SKIP_BYTES; }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait above).  ISX_NO_PDL=1 in the environment
+// falls back to fully serialised launches (A/B and bisecting aid).
+static bool pdl_enabled() {
+    static const bool on = getenv("ISX_NO_PDL") == nullptr;
+    return on;
+}
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_t st) {
     if (!d.traffic) return cudaSuccess;
     const int blocks = (d.E + DYN_WARPS - 1) / DYN_WARPS;
-    k_traffic<<<blocks, DYN_WARPS * 32, 0, st>>>(d, dt, spawn_prob);
-    return cudaGetLastError();
+    return launch_pdl(k_traffic, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
 }
 cudaError_t launch_ego(const Dev& d, const float* actions, float dt, cudaStream_t st) {
     const int NP = d.N <= 1 ? 1 : d.N <= 2 ? 2 : d.N <= 4 ? 4 : d.N <= 8 ? 8 : d.N <= 16 ? 16 : 32;
     const long long threads = ((long long)d.E * NP + 31) / 32 * 32;
     const int blocks = (int)((threads + EGO_THREADS - 1) / EGO_THREADS);
     switch (NP) {
-        case 1: k_ego<1><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
-        case 2: k_ego<2><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
-        case 4: k_ego<4><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
-        case 8: k_ego<8><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
-        case 16: k_ego<16><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
-        default: k_ego<32><<<blocks, EGO_THREADS, 0, st>>>(d, actions, dt); break;
+        case 1: return launch_pdl(k_ego<1>, blocks, EGO_THREADS, 0, st, d, actions, dt);
+        case 2: return launch_pdl(k_ego<2>, blocks, EGO_THREADS, 0, st, d, actions, dt);
+        case 4: return launch_pdl(k_ego<4>, blocks, EGO_THREADS, 0, st, d, actions, dt);
+        case 8: return launch_pdl(k_ego<8>, blocks, EGO_THREADS, 0, st, d, actions, dt);
+        case 16: return launch_pdl(k_ego<16>, blocks, EGO_THREADS, 0, st, d, actions, dt);
+        default: return launch_pdl(k_ego<32>, blocks, EGO_THREADS, 0, st, d, actions, dt);
     }
-    return cudaGetLastError();
 }
 cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float spawn_prob, cudaStream_t st) {
     cudaError_t e = launch_traffic(d, dt, spawn_prob, st);
@@ -943,18 +974,16 @@ cudaError_t launch_dynamics(const Dev& d, const float* actions, float dt, float 
 }
 cudaError_t launch_features(const Dev& d, int mode, cudaStream_t st) {
     const int agents = d.E * d.N;
-    k_features<<<(agents * 4 + FEAT_THREADS - 1) / FEAT_THREADS, FEAT_THREADS, 0, st>>>(d, mode);
-    return cudaGetLastError();
+    return launch_pdl(k_features, (agents * 4 + FEAT_THREADS - 1) / FEAT_THREADS, FEAT_THREADS, 0, st, d, mode);
 }
 cudaError_t launch_rays(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
     const long long total = (long long)d.E * d.N * d.R;
     const long long chunks = (total + LID_THREADS - 1) / LID_THREADS;
     const int grid = (int)(chunks < grid_cap ? chunks : grid_cap);
     const size_t sm = lidar_smem_bytes(d);
-    if (d.R == 72) k_lidar_obs<72><<<grid, LID_THREADS, sm, st>>>(d, mode);
-    else if (d.R == 96) k_lidar_obs<96><<<grid, LID_THREADS, sm, st>>>(d, mode);
-    else k_lidar_obs<0><<<grid, LID_THREADS, sm, st>>>(d, mode);
-    return cudaGetLastError();
+    if (d.R == 72) return launch_pdl(k_lidar_obs<72>, grid, LID_THREADS, sm, st, d, mode);
+    if (d.R == 96) return launch_pdl(k_lidar_obs<96>, grid, LID_THREADS, sm, st, d, mode);
+    return launch_pdl(k_lidar_obs<0>, grid, LID_THREADS, sm, st, d, mode);
 }
 cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
     cudaError_t e = launch_features(d, mode, st);

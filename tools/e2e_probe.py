@@ -53,6 +53,12 @@ def main():
         _lib.check(env._lib, env._lib.isx_step_pinned(env._h, C.c_float(1.0 / 60.0), env._stream()))
     tc = (time.perf_counter() - t0) / K
     print(f"isx_step_pinned alone (no Python staging): {tc * 1e6:.1f} us/step")
+    ms = (C.c_float * 64)()
+    for _ in range(3):
+        n = _lib.check(env._lib, env._lib.isx_pipe_timeline(env._h, C.c_float(1.0 / 60.0), env._stream(), ms, 16))
+    for i in range(n):
+        k0, k1, c0, c1 = (ms[4 * i + j] * 1e3 for j in range(4))
+        print(f"  range {i}: kernels {k0:7.1f} -> {k1:7.1f} us   copy {c0:7.1f} -> {c1:7.1f} us")
     print(f"step_host: {t * 1e6:.1f} us/step  -> {E * N / t:.3e} agent-steps/s;  obs D2H floor at the 1/1 rate above: see first line")
 
 
