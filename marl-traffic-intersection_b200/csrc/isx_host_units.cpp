@@ -100,6 +100,25 @@ void isxh_lidar(int lanes, int rays, const float* self_pose, const float* others
         dist[i] = best ? (float)(4 * best) : LIDAR_MAX_DIST;
     }
 }
+// Tuning probe: per beam of one ego, the march state after `lockstep` accelerated steps (k, or -1 when already done)
+// and the final road event index — what the cooperative tail of k_lidar_obs has left to do.
+void isxh_march_stats(int lanes, int rays, int lockstep, const float* self_pose, int* k_after, int* k_event) {
+    const RoadTables* t = tables_for(lanes);
+    std::vector<float> rel((size_t)rays);
+    lidar_rel_angles(rays, rel.data());
+    const RoadView rv{t->bits.data(), t->skip.data(), t->box_lo, t->box_hi};
+    for (int i = 0; i < rays; ++i) {
+        float s, c;
+        sincosf_(self_pose[2] + rel[i], &s, &c);
+        const Ray ray = make_ray(self_pose[0], self_pose[1], c, -s);
+        March m;
+        march_init(ray, m);
+        for (int it = 0; it < lockstep; ++it) if (!m.done) march_step(rv, ray, m);
+        k_after[i] = m.done ? -1 : m.k;
+        bool hit;
+        k_event[i] = ray_road_event(rv, ray, &hit);
+    }
+}
 int isxh_self_status(int lanes, float x, float y, float h, float gx, float gy, float px, float py) {
     return ego_self_status(lanes, x, y, h, F2{gx, gy}, F2{px, py});
 }

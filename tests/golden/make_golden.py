@@ -24,6 +24,11 @@ CASES = {
     "c4_eight": dict(num_lanes=3, ego_routes=R3[:8]),
     "c5_eight_traffic72": dict(num_lanes=3, ego_routes=R3[:8], traffic=True, density=1.0, lidar_rays=72),
     "two_lanes_norespawn": dict(num_lanes=2, ego_routes=po.ROUTES_2LANES[:3], traffic=True, density=2.0, respawn=False, max_steps=250),
+    # 20 egos on 12 spawn points + traffic: > 16 neighbours with exactly equal distances, the regime where
+    # IntersectionEnv.cpp:490's std::sort is not stable (libstdc++ introsort decides the order)
+    "stacked20_ties": dict(num_lanes=3, ego_routes=[R3[i % 12] for i in range(20)], traffic=True, density=3.0, lidar_rays=72, max_steps=150),
+    "four_lanes_team": dict(num_lanes=4, ego_routes=[("IN_1", "OUT_9"), ("IN_6", "OUT_15"), ("IN_11", "OUT_2"), ("IN_16", "OUT_4")], use_team=True,
+                            traffic=True, density=2.0),
 }
 STEPS, SEED, ENV_ID = 600, 20261018, 3
 
@@ -60,12 +65,38 @@ def run(env_cls, kw, steps=STEPS, seed=SEED, env_id=ENV_ID):
                 final_ego=np.stack([eg[f] for f in ("x", "y", "v", "heading", "steer", "prev_dist")]).astype(np.float32), **obs_keep)
 
 
+def sort_vectors():
+    """Key arrays and the rank order the toolchain's std::sort (libstdc++ 13, as linked into oracle/_ref) leaves them in:
+    tie-heavy random keys for every n in [0, 64) and McIlroy-adversary keys that force the heap-sort fallback."""
+    u = po.ref_unit()
+    rng = np.random.default_rng(11)
+    keys, perms = [], []
+    for n in list(range(0, 64)) * 4:
+        kind = rng.integers(0, 3)
+        k = (rng.integers(0, 3, n) if kind == 0 else rng.integers(0, max(n // 2, 1), n) if kind == 1 else rng.random(n)).astype(np.float32)
+        keys.append(k)
+    for n in range(17, 64):
+        base = u.sort_adversary(n)
+        keys += [base.copy(), np.floor(base / 2).astype(np.float32)]
+    for k in keys:
+        perms.append(u.std_sort(k)[0])
+    lens = np.array([len(k) for k in keys], np.int32)
+    return dict(lens=lens, keys=np.concatenate(keys).astype(np.float32), perms=np.concatenate(perms).astype(np.int32))
+
+
 def main():
     assert po.have_ref(), "oracle/_ref/libisx_ref.so missing: run `make -C oracle ref` where /root/reference exists"
+    only = set(sys.argv[1:])                      # python make_golden.py [case ...]: regenerate just these fixtures
+    if not only or "sort_vectors" in only:
+        np.savez_compressed(os.path.join(HERE, "sort_vectors.npz"), **sort_vectors())
     for name, kw in CASES.items():
+        if only and name not in only:
+            continue
         out = run(po.RefEnv, kw)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "status histogram", np.bincount(out["status"].ravel().astype(np.int64), minlength=6).tolist())
+    if only:
+        return
     # geometry + route golden
     u = po.ref_unit()
     geo = {}

@@ -99,3 +99,23 @@ def test_libm_points_match_this_machine():
     s, c = u.sincosf(g["a"])
     assert _same(s, g["sin"]) and _same(c, g["cos"]) and _same(u.tanf(g["a"]), g["tan"])
     assert _same(u.atan2f(g["a"], g["b"]), g["atan2"]) and _same(u.hypotf(g["a"], g["b"]), g["hypot"])
+
+
+def test_neighbor_sort_restatements_match_recorded_std_sort():
+    """The oracle's (and, when built, the product's host build of the) libstdc++ std::sort restatement against rank
+    orders recorded from the real std::sort — ties, > 16 elements, and adversary inputs that hit the heap fallback."""
+    g = np.load(os.path.join(GOLD, "sort_vectors.npz"))
+    units = [po.oracle_unit()]
+    hu = os.path.join(os.path.dirname(GOLD), "..", "marl-traffic-intersection_b200", "csrc", "libisx_host_units.so")
+    if os.path.exists(hu):
+        units.append(po.unit_of(hu, "isxh_"))
+    off = 0
+    fell_back = 0
+    for n in g["lens"]:
+        k, want = g["keys"][off:off + n], g["perms"][off:off + n]
+        off += n
+        for u in units:
+            got, heaps = u.std_sort(k)
+            assert (got == want).all(), (int(n), k.tolist())
+            fell_back += int(heaps or 0) > 0
+    assert fell_back > 0
