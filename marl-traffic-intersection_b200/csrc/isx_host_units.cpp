@@ -100,6 +100,11 @@ void isxh_lidar(int lanes, int rays, const float* self_pose, const float* others
         dist[i] = best ? (float)(4 * best) : LIDAR_MAX_DIST;
     }
 }
+// The angular beam window k_features computes for a car seen from an ego (ia, span; span 255 = all beams).
+void isxh_beam_window(const float* car_pose, float cx, float cy, float heading, int rays, int* ia, int* span) {
+    const BeamWindow w = beam_window(car_pixel_rect(car_pose[0], car_pose[1], car_pose[2]), cx, cy, heading, rays);
+    *ia = w.ia; *span = w.span;
+}
 // Tuning probe: per beam of one ego, the march state after `lockstep` accelerated steps (k, or -1 when already done)
 // and the final road event index — what the cooperative tail of k_lidar_obs has left to do.
 void isxh_march_stats(int lanes, int rays, int lockstep, const float* self_pose, int* k_after, int* k_event) {
