@@ -874,11 +874,11 @@ __global__ void k_reset(const Dev d, const uint8_t* __restrict__ mask) {
 }
 
 __global__ void k_reduce_stats(const Dev d) {
-    // one CTA; 64-bit sums of the per-env u32 counters, reward_sum in double
+    // one CTA of 1024 threads; 64-bit sums of the per-env u32 counters, reward_sum in double.  Fixed summation order
+    // (strided partials, then a shared-memory tree), so that the totals — reward_sum included — are bit-reproducible.
     __shared__ unsigned long long acc[STAT_SLOTS];
-    __shared__ double racc;
+    __shared__ double rpart[1024];
     if (threadIdx.x < STAT_SLOTS) acc[threadIdx.x] = 0;
-    if (threadIdx.x == 0) racc = 0.0;
     __syncthreads();
     unsigned long long loc[14];
     double r = 0.0;
@@ -888,12 +888,16 @@ __global__ void k_reduce_stats(const Dev d) {
         for (int i = 0; i < 14; ++i) loc[i] += st[i];
         r += *reinterpret_cast<const double*>(st + ST_RSUM);
     }
-    for (int i = 0; i < 14; ++i) atomicAdd(&acc[i], loc[i]);
-    atomicAdd(&racc, r);
+    for (int i = 0; i < 14; ++i) atomicAdd(&acc[i], loc[i]);       // integer sums: order does not matter
+    rpart[threadIdx.x] = r;
     __syncthreads();
+    for (int half = 512; half > 0; half >>= 1) {
+        if ((int)threadIdx.x < half && (int)threadIdx.x + half < (int)blockDim.x) rpart[threadIdx.x] += rpart[threadIdx.x + half];
+        __syncthreads();
+    }
     if (threadIdx.x < 14) d.stats[threadIdx.x] = acc[threadIdx.x];
     if (threadIdx.x == 14) d.stats[14] = 0;
-    if (threadIdx.x == 15) d.stats[15] = (unsigned long long)__double_as_longlong(racc);
+    if (threadIdx.x == 15) d.stats[15] = (unsigned long long)__double_as_longlong(rpart[0]);
 }
 
 // Masked restore of a snapshot (isx_snapshot_restore): thread per (env, array); copies the env's slice of the array.
