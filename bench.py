@@ -292,7 +292,7 @@ def main():
         counters = st
     counters = counters.cpu().tolist()
     stats = {"agent_steps": counters[11], "status_hist": counters[0:6], "npc_spawned": counters[6], "npc_removed": counters[7],
-             "npc_collided": counters[8], "npc_overflow": counters[9], "env_resets": counters[10]}
+             "npc_collided": counters[8], "npc_overflow": counters[9], "env_resets": counters[10], "neighbor_tie_sorts": counters[12]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
