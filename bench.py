@@ -153,6 +153,26 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- main
+def bind_to_gpu_numa_node(gpu_index: int) -> str:
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of
+    the host-buffer step (and the numpy copies into them) live on the GPU's own NUMA node.  Best effort: returns a short
+    description for the JSON line, never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 1)
+        local = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = sorted(local & allowed)
+        if not pick:
+            return f"unbound (GPU-local CPUs not in this process's {len(allowed)}-CPU set)"
+        os.sched_setaffinity(0, pick)
+        return f"{len(pick)} GPU-local CPUs of {len(allowed)}"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +211,8 @@ def main():
         raise SystemExit("bench.py (native arm) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    cpu_binding = bind_to_gpu_numa_node(local_rank)     # before the pinned staging buffers are allocated (first touch)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -296,6 +318,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)               # the CPU baseline gets every host core again
         try:
             threads = os.cpu_count() or 1
             v, _, info = cpu_reference_run(samples=10, warmup=1, steps_per_sample=400, threads=threads)
@@ -307,7 +330,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world, E),
+            "data": "synthetic", "config": dict(workload_config(world, E), host_cpu_binding=cpu_binding),
             "clocks": clocks, "gpu_launches": 4 * K,   # k_traffic, k_ego, k_features, k_lidar_obs per step
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "stats": stats, "wall_s_timed_region": t_wall,
