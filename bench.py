@@ -301,7 +301,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = E * N_AGENTS * Ke * world / float(te.item())
     h2d = E * N_AGENTS * 2 * 4
-    d2h = E * N_AGENTS * (127 * 4 + 4 + 1 + 1) + 2 * E
+    d2h = E * N_AGENTS * (127 * 4 + 4 + 1 + 1) + 2 * E + 2 * 4 * E     # obs, reward, done, status; terminated, truncated; agents_alive, step
 
     clocks = sampler.stop() if rank == 0 else None
 

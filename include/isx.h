@@ -165,6 +165,9 @@ int isx_step_host(isx_handle *h, const float *actions, float dt, float *obs, flo
 int isx_step_pinned(isx_handle *h, float dt, void *stream);
 int isx_host_views(isx_handle *h, float **actions, float **obs, float **reward, uint8_t **done, uint8_t **status,
                    uint8_t **terminated, uint8_t **truncated);
+/* Two more pinned views filled by the same step: agents_alive [E] and step [E] (int32), StepResult.agents_alive / .step
+ * of bindings.cpp:27-36. */
+int isx_host_views_aux(isx_handle *h, int32_t **agents_alive, int32_t **step);
 
 /* `steps` consecutive steps with actions drawn on the device from the Philox action stream
  * (DESIGN.md "RNG streams"); with auto_reset this is the random-action rollout BASELINE.json quotes. */

@@ -193,6 +193,10 @@ class BatchedIntersectionEnv:
                             reward=view(ptrs[2], (E, N), C.c_float, np.float32), done=view(ptrs[3], (E, N), C.c_uint8, np.uint8),
                             status=view(ptrs[4], (E, N), C.c_uint8, np.uint8), terminated=view(ptrs[5], (E,), C.c_uint8, np.uint8),
                             truncated=view(ptrs[6], (E,), C.c_uint8, np.uint8))
+            aux = [C.c_void_p(), C.c_void_p()]
+            _lib.check(self._lib, self._lib.isx_host_views_aux(self._h, C.byref(aux[0]), C.byref(aux[1])))
+            self._hv["agents_alive"] = view(aux[0], (E,), C.c_int32, np.int32)
+            self._hv["step"] = view(aux[1], (E,), C.c_int32, np.int32)
         return self._hv
 
     def step_host(self, actions: np.ndarray, dt: float = 1.0 / 60.0, copy: bool = False):

@@ -162,9 +162,10 @@ class IntersectionEnv:
         r.done = [int(x) for x in done[0]]
         r.status = [STATUS_NAMES[int(x)] for x in status[0]]
         r.agent_ids = list(range(1, n + 1))          # IntersectionEnv.cpp:130: 1..N after every reset
-        r.agents_alive = int(b.buf["agents_alive"][0].item())
+        hv = b._host_views()                           # pinned views filled by the same step: no extra device round trips
+        r.agents_alive = int(hv["agents_alive"][0])
         r.terminated, r.truncated = bool(term[0]), bool(trunc[0])
-        r.step = int(b.buf["step"][0].item())
+        r.step = int(hv["step"][0])
         self.step_count = r.step
         return r
 

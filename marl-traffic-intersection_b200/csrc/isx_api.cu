@@ -72,7 +72,7 @@ struct isx_handle {
     float* h_obs = nullptr; float* h_reward = nullptr;
     uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;   // views into h_small
     uint8_t *d_small = nullptr, *h_small = nullptr;      // reward | done | status | terminated | truncated, one block each side
-    size_t small_off[5] = {0, 0, 0, 0, 0}, small_bytes = 0;
+    size_t small_off[7] = {0, 0, 0, 0, 0, 0, 0}, small_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> ev_shard;                   // one per pipeline piece
     cudaStream_t pipe_stream = nullptr;                  // the captured host step replays here
@@ -294,19 +294,23 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
     ALLOC(d.epd, EN); ALLOC(d.epa0, EN); ALLOC(d.epa1, EN); ALLOC(d.epidx, EN); ALLOC(d.ealive, EN);
     ALLOC(d.nx, EM); ALLOC(d.ny, EM); ALLOC(d.nv, EM); ALLOC(d.nh, EM); ALLOC(d.nsteer, EM);
     ALLOC(d.npidx, EM); ALLOC(d.nroute, EM); ALLOC(d.nuid, EM);
-    ALLOC(d.ncount, E); ALLOC(d.next_uid, E); ALLOC(d.step_count, E); ALLOC(d.tick, E);
-    ALLOC(d.obs, EN * ISX_OBS_DIM); ALLOC(d.agents_alive, E);
+    ALLOC(d.ncount, E); ALLOC(d.next_uid, E); ALLOC(d.tick, E);
+    ALLOC(d.obs, EN * ISX_OBS_DIM);
     {
-        // reward | done | status | terminated | truncated live in ONE block (sub-arrays 256 B aligned), mirrored by one
-        // pinned host block, so the host-buffer step brings all of them back with a single copy
+        // reward | done | status | terminated | truncated | agents_alive | step live in ONE block (sub-arrays 256 B
+        // aligned), mirrored by one pinned host block, so the host-buffer step brings all of them back with a single copy
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         h->small_off[0] = 0;
         h->small_off[1] = up(sizeof(float) * EN);
         h->small_off[2] = h->small_off[1] + up(EN);
         h->small_off[3] = h->small_off[2] + up(EN);
         h->small_off[4] = h->small_off[3] + up(E);
-        h->small_bytes = h->small_off[4] + up(E);
+        h->small_off[5] = h->small_off[4] + up(E);
+        h->small_off[6] = h->small_off[5] + up(sizeof(int) * E);
+        h->small_bytes = h->small_off[6] + up(sizeof(int) * E);
         ALLOC(h->d_small, h->small_bytes);
+        d.agents_alive = reinterpret_cast<int*>(h->d_small + h->small_off[5]);
+        d.step_count = reinterpret_cast<int*>(h->d_small + h->small_off[6]);
         d.reward = reinterpret_cast<float*>(h->d_small + h->small_off[0]);
         d.done = h->d_small + h->small_off[1]; d.status = h->d_small + h->small_off[2];
         d.terminated = h->d_small + h->small_off[3]; d.truncated = h->d_small + h->small_off[4];
@@ -647,6 +651,13 @@ int isx_host_views(isx_handle* h, float** actions, float** obs, float** reward, 
     if (status) *status = h->h_status;
     if (terminated) *terminated = h->h_term;
     if (truncated) *truncated = h->h_trunc;
+    return ISX_OK;
+}
+
+int isx_host_views_aux(isx_handle* h, int32_t** agents_alive, int32_t** step) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (agents_alive) *agents_alive = reinterpret_cast<int32_t*>(h->h_small + h->small_off[5]);
+    if (step) *step = reinterpret_cast<int32_t*>(h->h_small + h->small_off[6]);
     return ISX_OK;
 }
 

@@ -54,8 +54,8 @@ class IntersectionEnv:
             reward_cfg = DEFAULT_REWARD_CONFIG.get("reward_config", {})
         if isinstance(reward_cfg, dict):
             _apply_reward_config(self.env, reward_cfg)
-        self.cars: List[cpp_backend.Car] = []
-        self.traffic_cars: List[cpp_backend.Car] = []
+        self._cars = None            # env.py:152,155,184 snapshot env.cars / env.traffic_cars eagerly; here the device
+        self._traffic_cars = None    # round trip (a sync + ~20 small copies) is paid only if somebody looks
         self.reset()
 
     @staticmethod
@@ -69,13 +69,26 @@ class IntersectionEnv:
         for i in range(self.num_agents):
             start_id, end_id = self.ego_routes[i]
             self.env.add_car_with_route(start_id, end_id)
-        self.cars = self.env.cars
-        if self.traffic_flow:
-            self.traffic_cars = list(self.env.traffic_cars)
+        self._cars = self.env.cars                      # reset-time snapshot, as env.py:152 (resets are rare)
+        self._traffic_cars = None
         obs = self._collect_obs()
         if self.traffic_flow:
             return obs[0], {}
         return obs, {}
+
+    @property
+    def cars(self) -> List["cpp_backend.Car"]:
+        """env.cars as of the last reset() (the reference keeps that list object, env.py:152)."""
+        return self._cars
+
+    @property
+    def traffic_cars(self) -> List["cpp_backend.Car"]:
+        """NPC snapshot after the last reset()/step() (env.py:155,184); empty without traffic_flow."""
+        if not self.traffic_flow:
+            return []
+        if self._traffic_cars is None:
+            self._traffic_cars = list(self.env.traffic_cars)
+        return self._traffic_cars
 
     def _collect_obs(self) -> np.ndarray:
         return np.asarray(self.env.get_observations(), dtype=np.float32)
@@ -90,8 +103,7 @@ class IntersectionEnv:
             else:
                 raise ValueError(f"Expected actions shape (N,2) for multi-agent, got {actions.shape}")
         res = self.env.step(actions[:, 0].tolist(), actions[:, 1].tolist(), float(dt))
-        if self.traffic_flow:
-            self.traffic_cars = list(self.env.traffic_cars)
+        self._traffic_cars = None                       # refetched on access (state cannot change between steps)
         obs = np.asarray(res.obs, dtype=np.float32)
         rewards = np.asarray(res.rewards, dtype=np.float32)
         terminated, truncated = bool(res.terminated), bool(res.truncated)
