@@ -73,6 +73,39 @@ def test_no_cpu_fallback():
     assert b"no CUDA device" in lib.isx_last_error()
 
 
+def test_config_validation_happens_before_any_device_work():
+    """Argument checks of isx_create / isx_create_groups need no GPU: bad sizes, bad ABI version, groups that disagree on
+    what shapes the shared buffers; a well-formed request then fails with ISX_E_CUDA on a box without a device."""
+    import torch
+    from marl_traffic_intersection_b200 import _lib
+    lib = _lib.load_library()
+    s, e = (C.c_char_p * 3)(b"IN_6", b"IN_4", b"IN_5"), (C.c_char_p * 3)(b"OUT_2", b"OUT_8", b"OUT_7")
+
+    def cfg(**kw):
+        c = _lib.Config()
+        c.abi_version, c.num_envs, c.num_agents, c.num_lanes, c.lidar_rays = 1, 4, 3, 3, 96
+        c.ego_start, c.ego_end = s, e
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    h = C.c_void_p()
+    for bad in (cfg(abi_version=99), cfg(num_envs=0), cfg(num_agents=0), cfg(num_agents=33), cfg(num_lanes=5), cfg(lidar_rays=0),
+                cfg(lidar_rays=97), cfg(npc_capacity=33), cfg(num_traffic_routes=-1)):
+        assert lib.isx_create(C.byref(bad), C.byref(h)) == _lib.E_ARG and not h.value
+    assert lib.isx_create(None, C.byref(h)) == _lib.E_ARG
+    two = (_lib.Config * 2)(cfg(), cfg(num_agents=2))
+    assert lib.isx_create_groups(two, 2, C.byref(h)) == _lib.E_ARG and b"same in every group" in lib.isx_last_error()
+    two = (_lib.Config * 2)(cfg(), cfg(lidar_rays=72))
+    assert lib.isx_create_groups(two, 2, C.byref(h)) == _lib.E_ARG
+    two = (_lib.Config * 2)(cfg(traffic_flow=1, npc_capacity=16), cfg(traffic_flow=1, npc_capacity=8))
+    assert lib.isx_create_groups(two, 2, C.byref(h)) == _lib.E_ARG and b"npc_capacity" in lib.isx_last_error()
+    assert lib.isx_create_groups(two, 0, C.byref(h)) == _lib.E_ARG and lib.isx_create_groups(two, 65, C.byref(h)) == _lib.E_ARG
+    if not torch.cuda.is_available():
+        ok = (_lib.Config * 2)(cfg(), cfg(num_lanes=2))
+        assert lib.isx_create_groups(ok, 2, C.byref(h)) == _lib.E_CUDA
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "marl-traffic-intersection_b200")
     for dp, _, files in os.walk(pkg):
