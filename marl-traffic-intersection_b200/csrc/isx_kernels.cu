@@ -42,6 +42,10 @@ constexpr int DYN_WARPS = ISX_DYN_WARPS;   // envs (warps) per CTA in k_traffic
 constexpr int EGO_THREADS = ISX_EGO_THREADS;
 constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
 constexpr int LID_THREADS = 256;
+#ifndef ISX_TRAFFIC_PACK2
+#define ISX_TRAFFIC_PACK2 1
+#endif
+constexpr bool TRAFFIC_PACK2 = ISX_TRAFFIC_PACK2 != 0;   // k_traffic<16>: two envs per warp when npc_capacity <= 16
 #ifndef ISX_WARP_GRAB
 #define ISX_WARP_GRAB 2
 #endif
@@ -102,18 +106,70 @@ struct NpcSmem {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// L = lanes per env.  L = 32: one env per warp, any NPC capacity.  L = 16 (npc_capacity <= 16, the default): TWO envs
+// share a warp, one per half — the mean env has ~1 NPC, so a whole warp per env runs its list-order chain on one or two
+// lanes; packing two envs into the same instruction stream halves the warps the latency-bound kernel has to retire.
+// Every warp-wide primitive below is group-wide: shuffles of width L, ballots masked to the group's half, loop bounds
+// made warp-uniform (max over the halves) with the body predicated per half.
+template <int L>
+struct Grp {
+    static constexpr unsigned MASK = L == 32 ? FULL : ((1u << (L & 31)) - 1u);
+    int shift;                                                        // first lane of my group within the warp
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(FULL, p) >> shift) & MASK; }
+    __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0u; }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(FULL, v, src, L); }
+    __device__ __forceinline__ float min_f(float v) const {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o, L));
+        return v;
+    }
+    __device__ __forceinline__ int umax(int v) const { return L == 32 ? v : max(v, __shfl_xor_sync(FULL, v, 16)); }   // warp-uniform bound
+};
+
+// Car::update_path_index with the 50-point window spread over the L lanes of a group; first minimum wins (Car.cpp:62-70).
+template <int L>
+__device__ __forceinline__ int group_path_index(const F2* __restrict__ path, int idx, float x, float y, int lane) {
+    const int start = idx < 0 ? 0 : idx;
+    const int end = min(start + 50, PATH_LEN);
+    float best = INFINITY;
+    int bi = start;
+#pragma unroll
+    for (int r = 0; r < (50 + L - 1) / L; ++r) {
+        const int i = start + lane + r * L;
+        if (i < end) {
+            const F2 p = path[i];
+            const float dx = p.x - x, dy = p.y - y;
+            const float d = dx * dx + dy * dy;
+            if (d < best) { best = d; bi = i; }
+        }
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, o, L);
+        const int oi = __shfl_xor_sync(FULL, bi, o, L);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    return bi;
+}
+
+template <int L>
 __global__ void __launch_bounds__(DYN_WARPS * 32, ISX_TRAFFIC_MINB)
 k_traffic(const Dev d, float dt, float spawn_prob) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ NpcSmem sm_all[DYN_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * DYN_WARPS + warp;
-    if (env >= d.E) return;                       // whole warp leaves; only warp-level sync below
-    NpcSmem& sm = sm_all[warp];
+    constexpr int EPW = 32 / L;                                       // envs per warp
+    __shared__ NpcSmem sm_all[DYN_WARPS * EPW];
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const int sub = wl / L, lane = wl % L;                            // `lane`: my lane within the env's group
+    const Grp<L> g{sub * L};
+    const int env_raw = (blockIdx.x * DYN_WARPS + warp) * EPW + sub;
+    if (env_raw - sub >= d.E) return;                                 // whole warp leaves; only warp-level sync below
+    const bool env_ok = env_raw < d.E;                                // an odd env count leaves the last half idle (c = 0, no writes)
+    const int env = env_ok ? env_raw : d.E - 1;
+    NpcSmem& sm = sm_all[warp * EPW + sub];
     const int N = d.N;
     const uint32_t genv = (uint32_t)(d.env_base + env);
-    int c = d.ncount[env];
+    int c = env_ok ? d.ncount[env] : 0;
     uint32_t next_uid = d.next_uid[env];
     const bool reset_now = d.auto_reset && (d.terminated[env] | d.truncated[env]);   // env.py:147-152 after a done step
     if (reset_now) { c = 0; next_uid = 1; }
@@ -130,33 +186,39 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         sm.steer[lane] = d.nsteer[ni]; sm.pidx[lane] = d.npidx[ni]; sm.route[lane] = d.nroute[ni]; sm.uid[lane] = d.nuid[ni];
     }
     __syncwarp();
-    // -- spawn draw (:321-329) and try_spawn_traffic_car (:275-315); every lane runs the same stream
+    // -- spawn draw (:321-329) and try_spawn_traffic_car (:275-315); every lane of the group runs the same stream
     TrafficStream ts;
     ts.init(d.seed, genv, tick);
-    if (ts.uniform01() < spawn_prob && d.T > 0) {
-        const int r = (int)ts.below((uint32_t)d.T);
-        evt.spawn_route = r;
-        const RouteMeta m = d.route_meta[N + r];
-        const float md = CAR_LENGTH * 2.5f, md2 = md * md;       // is_spawn_blocked (:240-259)
+    {
+        const bool want = env_ok && ts.uniform01() < spawn_prob && d.T > 0;
+        int r = 0;
         bool blk = false;
-        if (lane < N) {
-            float ex, ey;
-            if (reset_now) { const RouteMeta em = d.route_meta[lane]; ex = em.spawn_x; ey = em.spawn_y; }
-            else { ex = d.ex[env * N + lane]; ey = d.ey[env * N + lane]; }
-            const float dx = ex - m.spawn_x, dy = ey - m.spawn_y;
-            blk = dx * dx + dy * dy < md2;
+        RouteMeta m{};
+        if (want) {
+            r = (int)ts.below((uint32_t)d.T);
+            evt.spawn_route = r;
+            m = d.route_meta[N + r];
+            const float md = CAR_LENGTH * 2.5f, md2 = md * md;   // is_spawn_blocked (:240-259)
+            for (int a = lane; a < N; a += L) {
+                float ex, ey;
+                if (reset_now) { const RouteMeta em = d.route_meta[a]; ex = em.spawn_x; ey = em.spawn_y; }
+                else { ex = d.ex[env * N + a]; ey = d.ey[env * N + a]; }
+                const float dx = ex - m.spawn_x, dy = ey - m.spawn_y;
+                blk = blk || (dx * dx + dy * dy < md2);
+            }
+            if (lane < c) { const float dx = sm.x[lane] - m.spawn_x, dy = sm.y[lane] - m.spawn_y; blk = blk || (dx * dx + dy * dy < md2); }
         }
-        if (lane < c) { const float dx = sm.x[lane] - m.spawn_x, dy = sm.y[lane] - m.spawn_y; blk = blk || (dx * dx + dy * dy < md2); }
-        if (!__any_sync(FULL, blk)) {
+        const bool blocked = g.any(blk);
+        if (want && !blocked) {
             if (c < d.M) {
                 if (lane == 0) {
                     sm.x[c] = m.spawn_x; sm.y[c] = m.spawn_y; sm.v[c] = 0.0f; sm.h[c] = m.spawn_h; sm.steer[c] = 0.0f;
                     sm.pidx[c] = 0; sm.route[c] = r; sm.uid[c] = next_uid;
                 }
                 next_uid += 1; c += 1; evt.spawned = 1;
-                __syncwarp();
             } else overflow = 1;                                   // reference list is unbounded; counted
         }
+        __syncwarp();
     }
     evt.rng_draws = (int)ts.j;
     ISX_STAMP(1);
@@ -183,38 +245,42 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         my_tan = tanf_nc(my_steer);
     }
     ISX_STAMP(2);
-    for (int i = 0; i < c; ++i) {
+    const int cmax = g.umax(c);
+    for (int i = 0; i < cmax; ++i) {
+        const bool on = i < c;                                     // my group still has an NPC i
         Pose me;
-        me.x = __shfl_sync(FULL, cur.x, i); me.y = __shfl_sync(FULL, cur.y, i);
-        me.v = __shfl_sync(FULL, cur.v, i); me.h = __shfl_sync(FULL, cur.h, i);
-        const float ms = __shfl_sync(FULL, my_sin, i), mc = __shfl_sync(FULL, my_cos, i);
-        const float me_dc = __shfl_sync(FULL, my_dc, i), tan_s = __shfl_sync(FULL, my_tan, i);
-        const int mp0 = __shfl_sync(FULL, my_pidx, i);
-        const F2* path = d.route_path + (size_t)(N + __shfl_sync(FULL, my_route, i)) * PATH_LEN;
+        me.x = g.shfl(cur.x, i); me.y = g.shfl(cur.y, i);
+        me.v = g.shfl(cur.v, i); me.h = g.shfl(cur.h, i);
+        const float ms = g.shfl(my_sin, i), mc = g.shfl(my_cos, i);
+        const float me_dc = g.shfl(my_dc, i), tan_s = g.shfl(my_tan, i);
+        const int mp0 = g.shfl(my_pidx, i);
+        const F2* path = d.route_path + (size_t)(N + g.shfl(my_route, i)) * PATH_LEN;
         float fc = 1e9f;
         int flags = 0;
-        if (lane < c && lane != i) {
+        if (on && lane < c && lane != i) {
             fc = npc_front_candidate(me, cur, ms, mc);
             flags = npc_pair_flags(me, cur, ms, mc, me_dc, i < lane);
         }
         if (i == 0) ISX_STAMP(8);
-        const float thr0 = npc_cruise_throttle(me.v, warp_min_f(fc));
-        const unsigned elig = __ballot_sync(FULL, flags & 1);
-        const unsigned yld = __ballot_sync(FULL, flags & 2);
+        const float thr0 = npc_cruise_throttle(me.v, g.min_f(fc));
+        const unsigned elig = g.ballot(flags & 1);
+        const unsigned yld = g.ballot(flags & 2);
         bool conflict = false;
         float min_conf = 1e9f;
-        if (elig) {                                                // ghost-path scan (:91-185), 32 points per pass
+        if (__any_sync(FULL, elig != 0u)) {                        // ghost-path scan (:91-185), L points per pass
             const float safe_sq = (CAR_WIDTH * 2.0f) * (CAR_WIDTH * 2.0f);
             const int s1 = min(mp0 + 120, PATH_LEN);
-            for (int base = mp0; base < s1 && !conflict; base += 32) {
-                const int g = base + lane;
+            for (int base = mp0;; base += L) {
+                const bool go = elig != 0u && base < s1 && !conflict;
+                if (!__any_sync(FULL, go)) break;
+                const int gp_i = base + lane;
                 bool hit = false;
                 float dtc = 0.0f;
-                if (g < s1) {
-                    const F2 gp = path[g];
+                if (go && gp_i < s1) {
+                    const F2 gp = path[gp_i];
                     unsigned near_yield = 0, near_any = 0;
-                    for (unsigned m = elig; m; m &= m - 1) {
-                        const int o = __ffs(m) - 1;
+                    for (unsigned mm = elig; mm; mm &= mm - 1) {
+                        const int o = __ffs(mm) - 1;
                         const float dx = sm.x[o] - gp.x, dy = sm.y[o] - gp.y;
                         if (dx * dx + dy * dy < safe_sq) { near_any = 1; near_yield |= (yld >> o) & 1u; }
                     }
@@ -223,18 +289,19 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
                         hit = near_yield || (dtc < 15.0f);
                     }
                 }
-                const unsigned hb = __ballot_sync(FULL, hit);
-                if (hb) { conflict = true; min_conf = __shfl_sync(FULL, dtc, __ffs(hb) - 1); }
+                const unsigned hb = g.ballot(hit);
+                const float first_dtc = g.shfl(dtc, hb ? __ffs(hb) - 1 : 0);
+                if (hb) { conflict = true; min_conf = first_dtc; }
             }
         }
         if (i == 0) ISX_STAMP(9);
         const float thr = npc_final_throttle(thr0, conflict, min_conf);
         float macc = 0.0f;
-        car_motion_update(me, macc, thr, tan_s, dt);               // every lane, same operands: uniform
+        car_motion_update(me, macc, thr, tan_s, dt);               // every lane of the group, same operands: uniform
         if (i == 0) ISX_STAMP(10);
-        const int mp = warp_path_index(path, mp0, me.x, me.y, lane);
+        const int mp = group_path_index<L>(path, mp0, me.x, me.y, lane);
         if (i == 0) ISX_STAMP(11);
-        if (lane == i) { cur = me; my_pidx = mp; sm.x[i] = me.x; sm.y[i] = me.y; }
+        if (on && lane == i) { cur = me; my_pidx = mp; sm.x[i] = me.x; sm.y[i] = me.y; }
         __syncwarp();
     }
     if (lane < c) { sm.v[lane] = cur.v; sm.h[lane] = cur.h; sm.steer[lane] = my_steer; sm.pidx[lane] = my_pidx; }
@@ -244,11 +311,11 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     // -- NPC-NPC collisions (:347-356): lane j tests the pair (i, j), j > i
     unsigned alive_m = c >= 32 ? FULL : ((1u << c) - 1u);
     const unsigned all_m = alive_m;
-    for (int i = 0; i + 1 < c; ++i) {
+    for (int i = 0; i + 1 < cmax; ++i) {
         bool hit = false;
         if (lane > i && lane < c) hit = cars_collide(sm.x[i], sm.y[i], sm.h[i], sm.x[lane], sm.y[lane], sm.h[lane]);
-        const unsigned hm = __ballot_sync(FULL, hit);
-        if ((alive_m >> i) & 1u) {
+        const unsigned hm = g.ballot(hit);
+        if (i + 1 < c && ((alive_m >> i) & 1u)) {
             const unsigned m = hm & alive_m;
             if (m) alive_m &= ~(m | (1u << i));
         }
@@ -265,7 +332,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         const bool oos = mx < -100.0f || mx > (float)WIDTH + 100.0f || my < -100.0f || my > (float)HEIGHT + 100.0f;
         rem = !((alive_m >> lane) & 1u) || arrived || oos;
     }
-    const unsigned rem_m = __ballot_sync(FULL, rem);
+    const unsigned rem_m = g.ballot(rem);
     evt.removed_mask = rem_m;
     evt.collided_mask = all_m & ~alive_m;
     const unsigned keep_m = all_m & ~rem_m;
@@ -279,10 +346,10 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     }
     c = __popc(keep_m);
     evt.npc_count = c;
-    if (lane == 0) { d.ncount[env] = c; d.next_uid[env] = next_uid; d.events[env] = evt; }
+    if (env_ok && lane == 0) { d.ncount[env] = c; d.next_uid[env] = next_uid; d.events[env] = evt; }
     ISX_STAMP(5);
-    if (d.trace && lane == 0) d.trace[(size_t)env * 16 + 6] = c;
-    {
+    if (d.trace && env_ok && lane == 0) d.trace[(size_t)env * 16 + 6] = c;
+    if (env_ok) {
         uint32_t* st = d.env_stats + (size_t)env * STAT_SLOTS;
         uint32_t inc = 0;
         if (lane == ST_SPAWNED) inc = (uint32_t)evt.spawned;
@@ -957,8 +1024,12 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 
 cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_t st) {
     if (!d.traffic) return cudaSuccess;
+    if (d.M <= 16 && TRAFFIC_PACK2) {                // two envs per warp (the default capacity)
+        const int blocks = (d.E + 2 * DYN_WARPS - 1) / (2 * DYN_WARPS);
+        return launch_pdl(k_traffic<16>, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
+    }
     const int blocks = (d.E + DYN_WARPS - 1) / DYN_WARPS;
-    return launch_pdl(k_traffic, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
+    return launch_pdl(k_traffic<32>, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
 }
 cudaError_t launch_ego(const Dev& d, const float* actions, float dt, cudaStream_t st) {
     const int NP = d.N <= 1 ? 1 : d.N <= 2 ? 2 : d.N <= 4 ? 4 : d.N <= 8 ? 8 : d.N <= 16 ? 16 : 32;
