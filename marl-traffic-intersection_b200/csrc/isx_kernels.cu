@@ -258,8 +258,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         float fc = 1e9f;
         int flags = 0;
         if (on && lane < c && lane != i) {
-            fc = npc_front_candidate(me, cur, ms, mc);
-            flags = npc_pair_flags(me, cur, ms, mc, me_dc, i < lane);
+            flags = npc_pair_eval(me, cur, ms, mc, me_dc, i < lane, &fc);
         }
         if (i == 0) ISX_STAMP(8);
         const float thr0 = npc_cruise_throttle(me.v, g.min_f(fc));

@@ -475,13 +475,24 @@ ISX_HD bool beam_in_window(const BeamWindow& w, int i, int R) {
 // Pairwise, ghost-index-independent part of the yield logic for NPC `me` against NPC `ot`:
 //   bit0 : `ot` can conflict at all (not same-direction < 60 deg :103-104, not a stable side-by-side car :107-159)
 //   bit1 : yield rules 2-4 hold (:167-176); rule 1 (dist_to_crash < 15) depends on the ghost point.
-ISX_HD_NOINL int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, float me_cos, float me_dc, bool me_before_ot) {
-    const float ad = fabsf(wrap_angle(me.h - ot.h));
-    if (ad < (60.0f * PI_F / 180.0f)) return 0;
+// What NPC `me` needs to know about one other NPC `ot` when it plans (TrafficFlow.cpp): the other's contribution to
+// get_front_car_dist_tf (:28-44) in *front (its distance, or 1e9), and the conflict flags of :91-185 as the return value
+// (bit 0: eligible for the ghost-path scan, bit 1: me yields to it).  One function because both start from the same
+// centre distance hypot(dx, dy) and the same |wrap(me.h - ot.h)| — on the list-order critical path of k_traffic a
+// second hypot + fmod per NPC is ~10% of the step of the busiest env.
+ISX_HD_NOINL int npc_pair_eval(const Pose& me, const Pose& ot, float me_sin, float me_cos, float me_dc, bool me_before_ot, float* front) {
     const float dxt = ot.x - me.x, dyt = ot.y - me.y;
-    const float dto = hypotf_nc(dxt, dyt);
+    const float dto = hypotf_(dxt, dyt);
+    const float ad = fabsf(wrap_angle(me.h - ot.h));
+    const float mx = me_cos, my = -me_sin;
+    float f = 1e9f;
+    if (!(dto > 80.0f)) {
+        const float dot = (dxt * mx + dyt * my) / (dto + 1e-5f);
+        if (dot > 0.8f && ad < (45.0f * PI_F / 180.0f)) f = dto;
+    }
+    *front = f;
+    if (ad < (60.0f * PI_F / 180.0f)) return 0;
     if (dto > 1e-5f) {
-        const float mx = me_cos, my = -me_sin;
         const float adn = fminf(ad, 2.0f * PI_F - ad);
         const bool parallel = (adn < (30.0f * PI_F / 180.0f)) || (adn > (150.0f * PI_F / 180.0f));
         if (parallel) {
@@ -509,20 +520,6 @@ ISX_HD_NOINL int npc_pair_flags(const Pose& me, const Pose& ot, float me_sin, fl
     else if (ot_dc < me_dc - 5.0f) y = true;
     else if (fabsf(ot_dc - me_dc) <= 5.0f) y = me_before_ot;
     return 1 | (y ? 2 : 0);
-}
-
-// get_front_car_dist_tf contribution of one other NPC (TrafficFlow.cpp:28-44): its distance, or 1e9.
-ISX_HD float npc_front_candidate(const Pose& me, const Pose& ot, float me_sin, float me_cos) {
-    const float dx = ot.x - me.x, dy = ot.y - me.y;
-    const float d = hypotf_nc(dx, dy);
-    if (d > 80.0f) return 1e9f;
-    const float vx = me_cos, vy = -me_sin;
-    const float dot = (dx * vx + dy * vy) / (d + 1e-5f);
-    if (dot > 0.8f) {
-        const float ad = fabsf(wrap_angle(me.h - ot.h));
-        if (ad < (45.0f * PI_F / 180.0f)) return d;
-    }
-    return 1e9f;
 }
 
 // Lateral P-control + cruise thresholds + front-car braking (TrafficFlow.cpp:50-75).
