@@ -57,33 +57,6 @@ constexpr int LOCKSTEP = ISX_LOCKSTEP;     // accelerated march steps every lane
 constexpr int ROAD_BITS_BYTES = ((ROAD_ROWS * ROAD_WORDS * 4 + 15) / 16) * 16;
 constexpr int ROAD_SKIP_BYTES = ((SKIP_DIM * SKIP_DIM + 15) / 16) * 16;
 
-__device__ __forceinline__ float warp_min_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
-// Car::update_path_index with the 50-point window spread over the lanes; first minimum wins (Car.cpp:62-70).
-__device__ __forceinline__ int warp_path_index(const F2* __restrict__ path, int idx, float x, float y, int lane) {
-    const int start = idx < 0 ? 0 : idx;
-    const int end = min(start + 50, PATH_LEN);
-    float best = INFINITY;
-    int bi = start;
-    for (int i = start + lane; i < end; i += 32) {
-        const F2 p = path[i];
-        const float dx = p.x - x, dy = p.y - y;
-        const float d = dx * dx + dy * dy;
-        if (d < best) { best = d; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(FULL, best, o);
-        const int oi = __shfl_xor_sync(FULL, bi, o);
-        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    return bi;
-}
-
 #define ISX_STAMP(slot) do { if (d.trace && lane == 0) d.trace[(size_t)env * 16 + (slot)] = clock64(); } while (0)
 
 struct NpcSmem {
@@ -93,11 +66,7 @@ struct NpcSmem {
     uint32_t coll[ISX_MAX_NPC];
 };
 
-// ------------------------------------------------------------------------------------------------ k_traffic
-// NPC traffic flow (TrafficFlow.cpp:317-367), one WARP per env: spawn draw, Gauss-Seidel planner/integrator in list
-// order, NPC-NPC SAT, ordered erase.  The lanes spread over path-window points / other NPCs / ghost-path points.
-// Reads the egos' PRE-step positions (spawn blocking, :244-249), so it runs before k_ego.  Only launched when traffic
-// flow is enabled.
+// ------------------------------------------------------------------------------------------------ launch chaining
 // Programmatic dependent launch (sm_90+): the four step kernels are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of kernel k+1 may become resident while kernel k drains
 // its last wave.  Every kernel first lets ITS successor start (launch_dependents), runs whatever does not depend on the
@@ -106,6 +75,11 @@ struct NpcSmem {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------ k_traffic
+// NPC traffic flow (TrafficFlow.cpp:317-367), one group of L lanes per env: spawn draw, Gauss-Seidel planner/integrator
+// in list order, NPC-NPC SAT, ordered erase.  The lanes spread over path-window points / other NPCs / ghost-path points.
+// Reads the egos' PRE-step positions (spawn blocking, :244-249), so it runs before k_ego.  Only launched when traffic
+// flow is enabled.
 // L = lanes per env.  L = 32: one env per warp, any NPC capacity.  L = 16 (npc_capacity <= 16, the default): TWO envs
 // share a warp, one per half — the mean env has ~1 NPC, so a whole warp per env runs its list-order chain on one or two
 // lanes; packing two envs into the same instruction stream halves the warps the latency-bound kernel has to retire.
