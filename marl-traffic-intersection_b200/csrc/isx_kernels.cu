@@ -568,20 +568,15 @@ k_features(const Dev d, int mode) {
         // ---- beam candidates.  Lidar.cpp:57-63: the ego itself, and anything within 1e-3 of its pose, is transparent;
         //      beams reach at most 248 px (+1 px truncation) from the origin pixel
         bool is_cand = false;
-        uint32_t packed = 0;
         if (have && mode == LIDAR_MARCH) {
             const bool same = fabsf(ox - me.x) < 1e-3f && fabsf(oy - me.y) < 1e-3f && fabsf(oh - me.h) < 1e-3f;
             if (!same) {
                 const PixRect r = rects[k];        // written by k_ego / k_traffic earlier in this step
-                if (!(r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250)) {
-                    const BeamWindow w = beam_window(r, me.x, me.y, me.h, R);
-                    packed = (uint32_t)k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16);
-                    is_cand = true;
-                }
+                is_cand = !(r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250);
             }
         }
         const unsigned qb = (__ballot_sync(FULL, is_cand) >> qshift) & 0xFu;      // this quad's votes, in car order
-        if (is_cand) cand[ncand + __popc(qb & ((1u << q) - 1u))] = packed;
+        if (is_cand) cand[ncand + __popc(qb & ((1u << q) - 1u))] = (uint32_t)k;   // the beam window is added below
         ncand += __popc(qb);
         // ---- own part of the five nearest other alive cars (ascending distance, ties by list order; stable, :466-492)
         if (have && k != self && k_alive) {
@@ -598,6 +593,16 @@ k_features(const Dev d, int mode) {
         }
     }
     if (ok && q == 0) d.cand_n[ga] = ncand;
+    // Beam windows of the compacted candidates, four at a time: ~300 instructions each (atan2 + two atan), so they run on
+    // the dense list — every lane of the quad busy — rather than inside the sparse in-range test above.
+    __syncwarp();
+    if (ok) {
+        for (int e = q; e < ncand; e += 4) {
+            const uint32_t k = cand[e];
+            const BeamWindow w = beam_window(rects[k], me.x, me.y, me.h, R);
+            cand[e] = k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16);
+        }
+    }
     float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
     // ---- merge the four sorted partial lists: five rounds of a quad-wide lexicographic (distance, list index) minimum,
     //      plus a sixth minimum that is only looked at for the tie test below
