@@ -30,10 +30,10 @@ constexpr unsigned FULL = 0xffffffffu;
 #define ISX_FEAT_THREADS 128
 #endif
 #ifndef ISX_TRAFFIC_MINB
-#define ISX_TRAFFIC_MINB 1
-#endif
+#define ISX_TRAFFIC_MINB 32   // 32-thread CTAs: 32 per SM = 64 registers (16 words of spill): neutral at 8192 envs, where the
+#endif                        // longest env chain sets the time, 145 -> 132 us at 65536 envs, where resident warps do
 #ifndef ISX_EGO_MINB
-#define ISX_EGO_MINB 1
+#define ISX_EGO_MINB 8        // 64 registers, no spills (76.3 -> 75.1 us at 65536 envs; tighter caps spill and lose)
 #endif
 #ifndef ISX_FEAT_MINB
 #define ISX_FEAT_MINB 8     // k_features is latency-bound: capping it at 63 registers (no spills) lets 8 CTAs instead of 5 share
