@@ -36,8 +36,8 @@ constexpr unsigned FULL = 0xffffffffu;
 #define ISX_EGO_MINB 8        // 64 registers, no spills (76.3 -> 75.1 us at 65536 envs; tighter caps spill and lose)
 #endif
 #ifndef ISX_FEAT_MINB
-#define ISX_FEAT_MINB 8     // k_features is latency-bound: capping it at 63 registers (no spills) lets 8 CTAs instead of 5 share
-#endif                      // an SM (measured 30.9 -> 26.8 us at 8192x8; the same cap costs k_ego spills and time, so not there)
+#define ISX_FEAT_MINB 12    // k_features is latency-bound: 40 registers (11 words of spill) let 12 CTAs instead of 5 share an SM
+#endif                      // (8192x8: 30.9 -> 25 us; 65536x8: 151 -> 139 us; 16 CTAs / 32 registers spill too much: 148 us)
 constexpr int DYN_WARPS = ISX_DYN_WARPS;   // envs (warps) per CTA in k_traffic
 constexpr int EGO_THREADS = ISX_EGO_THREADS;
 constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
