@@ -1,44 +1,53 @@
 #!/usr/bin/env python
-"""Grouped (per function) view on top of tools/ncu_lines.py:  python tools/ncu_groups.py <rep> <kernel> [mangled]"""
-import os, re, subprocess, sys
+"""Per-FUNCTION view of an ncu report, on top of tools/ncu_lines.py:
+
+    python tools/ncu_groups.py <rep> <kernel> [mangled-substring]
+
+Every profiled source line is attributed to the function whose definition encloses it in the current sources (found by
+scanning upwards for a definition line at column 0), so the table follows the code as it is refactored."""
+import collections
+import os
+import re
+import subprocess
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "marl-traffic-intersection_b200", "csrc")
 rep, kern = sys.argv[1], sys.argv[2]
 mangled = sys.argv[3] if len(sys.argv) > 3 else kern
-txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kern, "100000", mangled], stdout=subprocess.PIPE, text=True).stdout
-def marks(path, names):
-    src = open(path).read().splitlines()
-    out = []
-    for label, needle in names:
-        for i, l in enumerate(src):
-            if needle in l:
-                out.append((label, i + 1)); break
-    return sorted(out, key=lambda x: x[1])
-C = os.path.join(ROOT, "marl-traffic-intersection_b200", "csrc")
-sim = marks(os.path.join(C, "isx_sim.cuh"), [("on_road/geom", "ISX_HD bool on_road"), ("car_update", "ISX_HD void car_update"), ("corners/sat", "ISX_HD void car_corners"),
-    ("path_index_update", "ISX_HD int path_index_update"), ("ego_self_status", "ISX_HD int ego_self_status"), ("reward_base", "ISX_HD float reward_base"),
-    ("car_pixel_rect", "ISX_HD PixRect car_pixel_rect"), ("ray_pixel", "ISX_HD void ray_pixel"), ("road_bit/skip", "ISX_HD bool road_bit"),
-    ("rcp/make_ray/axis_exit", "ISX_HD float approx_rcp"), ("march_init", "ISX_HD void march_init"), ("sample_event", "ISX_HD int sample_event"),
-    ("march_step", "ISX_HD void march_step"), ("ray_road_event", "ISX_HD int ray_road_event"), ("ray_rect_first_hit", "ISX_HD int ray_rect_first_hit"),
-    ("beam_window", "ISX_HD BeamWindow beam_window"), ("npc_pair_flags", "ISX_HD int npc_pair_flags"), ("npc_front/steer/throttle", "ISX_HD float npc_front_candidate"),
-    ("obs features", "ISX_HD void obs_ego_features")])
-ker = marks(os.path.join(C, "isx_kernels.cu"), [("warp helpers", "warp_min_f"), ("dyn: load/reset", "k_dynamics(const Dev d"), ("dyn: traffic load+spawn", "traffic flow (TrafficFlow.cpp:317-367)"),
-    ("dyn: npc loop", "NPC controller, sequential in list order"), ("dyn: npc collisions", "NPC-NPC collisions (:347-356)"), ("dyn: npc erase", "ordered erase of dead"),
-    ("dyn: ego update+pathidx", "egos (IntersectionEnv.cpp:144-370)"), ("dyn: ego car-car", "car-car override (:293-318)"), ("dyn: bonuses..term", "terminal bonuses (:321-326)"),
-    ("dyn: writeback+stats", "---- write back"), ("lid: warp_road_event", "int warp_road_event("), ("lid: setup/stage", "k_lidar_obs(const Dev d"),
-    ("lid: features", "per ego: candidate set"), ("lid: beams", "beams: one thread per (ego, beam)"), ("small kernels", "small kernels")])
-tot, total = {}, 0
+txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kern, "100000", mangled],
+                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+DEF = re.compile(r"^(?:ISX_HD\w*|__device__|__global__|template|static|inline|struct)[^;]*?\b(\w+)\s*(?:\(|\{)")
+KERN = re.compile(r"^(k_\w+)\(")
+sources = {}
+
+
+def function_of(fname, line):
+    path = os.path.join(CSRC, fname)
+    if fname not in sources:
+        sources[fname] = open(path, errors="ignore").read().split("\n") if os.path.exists(path) else None
+    src = sources[fname]
+    if src is None:
+        return fname
+    for i in range(min(line, len(src)) - 1, -1, -1):
+        m = KERN.match(src[i]) or (DEF.match(src[i]) if not src[i].startswith(" ") else None)
+        if m:
+            return m.group(1)
+    return fname
+
+
+inst, samp, lanes = collections.Counter(), collections.Counter(), collections.Counter()
 for ln in txt.splitlines():
     m = re.match(r"(\S+):(\d+)\s+([\d,]+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)", ln)
-    if not m: continue
-    f, l, wi, thr, samp = m.group(1), int(m.group(2)), int(m.group(3).replace(",", "")), float(m.group(5)), float(m.group(6))
-    total += wi
-    key = f
-    for name, table in (("isx_sim.cuh", sim), ("isx_kernels.cu", ker)):
-        if f == name:
-            key = name + ":?"
-            for label, start in table:
-                if l >= start: key = label
-    t = tot.setdefault(key, [0, 0.0, 0.0]); t[0] += wi; t[1] += wi * thr; t[2] += samp
-print(txt.splitlines()[0])
-for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0]):
-    print(f"{k:32s} {v[0]:12,d} {100 * v[0] / total:5.1f}%  thr/inst {v[1] / max(v[0], 1):5.1f}  samples {v[2]:5.1f}%")
+    if not m:
+        continue
+    f, l, c, thr, sp = m.group(1), int(m.group(2)), int(m.group(3).replace(",", "")), float(m.group(5)), float(m.group(6))
+    k = function_of(f, l)
+    inst[k] += c
+    samp[k] += sp
+    lanes[k] += c * thr
+tot = sum(inst.values()) or 1
+print(txt.splitlines()[0] if txt else "no data")
+print(f"{'function':34s} {'%inst':>7s} {'%samples':>9s} {'lanes/inst':>10s}")
+for k, v in inst.most_common(24):
+    print(f"{k:34s} {100 * v / tot:7.2f} {samp[k]:9.2f} {lanes[k] / max(v, 1):10.1f}")
