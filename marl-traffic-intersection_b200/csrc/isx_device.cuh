@@ -48,7 +48,7 @@ struct Dev {
     // ---- k_features -> k_lidar_obs scratch
     void* agent_rec;             // [E][N] AgentRec {x, y, heading, rect_base | -1}
     void* car_rect;              // [E][N+M] PixRect (lidar pixel rectangle of every car)
-    uint32_t* cand;              // [E][N][N+M] packed beam candidates: car | first beam << 8 | span << 16
+    uint32_t* cand;              // [E][N][N+M] packed beam candidates: car | first beam << 8 | span << 16 | kmin << 24
     int* cand_n;                 // [E][N]
     unsigned* ray_counter;       // [1] dynamic work counter of k_lidar_obs
     // ---- outputs

@@ -92,6 +92,7 @@ void isxh_lidar(int lanes, int rays, const float* self_pose, const float* others
                 const PixRect& r = rects[q];
                 const int lim = best ? best - 1 : kmax;
                 if (lim < 1) break;
+                if (wins[q].kmin > lim) continue;                     // range pruning, as the kernel does
                 if (!beam_in_window(wins[q], i, rays)) continue;      // angular pruning, as the kernel does
                 const int k = ray_rect_first_hit(r, ray, lim);
                 if (k) best = k;

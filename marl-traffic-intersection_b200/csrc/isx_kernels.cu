@@ -600,7 +600,7 @@ k_features(const Dev d, int mode) {
         for (int e = q; e < ncand; e += 4) {
             const uint32_t k = cand[e];
             const BeamWindow w = beam_window(rects[k], me.x, me.y, me.h, R);
-            cand[e] = k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16);
+            cand[e] = k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16) | ((uint32_t)w.kmin << 24);
         }
     }
     float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
@@ -773,9 +773,10 @@ k_lidar_obs(const Dev d, int mode) {
                     const int iw = (i == R - 1) ? 0 : i;        // beam R-1 duplicates beam 0
                     for (int j = 0; j < nc && lim >= 1; ++j) {
                         const uint32_t ci = cand[j];
+                        if ((int)(ci >> 24) > lim) continue;     // the car lies beyond what this beam can still see (kmin)
                         int dlt = iw - (int)((ci >> 8) & 255u);  // angular window of this car (beam_window); span 255 = all
                         dlt += (dlt >> 31) & (R - 1);
-                        if (dlt > (int)(ci >> 16)) continue;
+                        if (dlt > (int)((ci >> 16) & 255u)) continue;
                         const int kh = ray_rect_first_hit(rects[rec.rect_base + (int)(ci & 255u)], ray, lim);
                         if (kh) { best = kh; lim = kh - 1; }
                     }

@@ -422,22 +422,28 @@ ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
 // ego at distance D > rho that disc spans +-asin(rho/D) <= +-(x + 0.5708 x^3), x = rho/D.  Beam i (i < R-1) points
 // at relative angle -pi + i*2pi/(R-1); beam R-1 duplicates beam 0.  The window is widened by one beam on each
 // side (0.065..0.088 rad, against ~1e-6 rad of rounding).  span = 255 means "every beam".
-struct BeamWindow { int ia, span; };
+struct BeamWindow { int ia, span, kmin; };
 // Conservative set of beams that can touch a car's pixel rectangle, as a circular index interval [ia, ia + span]
 // (mod R-1; beam R-1 duplicates beam 0; span 255 = every beam).  The rectangle, grown by 1.01 px for the truncation of
 // sample positions to pixels, is seen from the origin under the angles of its silhouette corners: with a = centre
 // direction, the offset of corner b is atan(a x b / a . b) (the origin is outside the bounding circle, so |offset| <
 // 90 deg and a . b > 0).  Approximate libm / reciprocal are fine: the interval is widened by MARGIN beams (0.25 deg at
 // 72 beams, >1000x their error) and every candidate sample is verified exactly by ray_rect_first_hit.
+// kmin: no sample before index kmin can lie in the rectangle — a sample sits 4k px from the origin and within 1 px per
+// axis of its pixel, so 4k >= (distance to the centre) - (half diagonal of the grown rectangle); half a pixel of slack.
 ISX_HD_NOINL BeamWindow beam_window(const PixRect& r, float cx, float cy, float heading, int R) {
     BeamWindow w;
-    w.ia = 0; w.span = 255;
+    w.ia = 0; w.span = 255; w.kmin = 0;
     if (R < 4) return w;
     const float hx = 0.5f * (float)(r.x1 - r.x0) + 1.01f, hy = 0.5f * (float)(r.y1 - r.y0) + 1.01f;
     const float ccx = 0.5f * (float)(r.x0 + r.x1), ccy = 0.5f * (float)(r.y0 + r.y1);
     const float X = ccx - cx, Y = ccy - cy;
     const float D2 = X * X + Y * Y, rho2 = hx * hx + hy * hy;
     if (!(D2 > rho2 * 1.05f + 1.0f)) return w;
+    {
+        const int km = (int)floorf((sqrtf(D2) - sqrtf(rho2) - 0.5f) * 0.25f);
+        w.kmin = km < 0 ? 0 : (km > 255 ? 255 : km);
+    }
     float tmin = 0.0f, tmax = 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
