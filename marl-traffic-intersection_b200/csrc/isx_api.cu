@@ -364,6 +364,10 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         if (e == cudaSuccess) e = lidar_occupancy(d, &per_sm);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         if (e != cudaSuccess || per_sm < 1) { isx_destroy(h); return fail(ISX_E_CUDA, "lidar kernel cannot be scheduled: %s", cudaGetErrorString(e)); }
+        if (const char* cap = getenv("ISX_LIDAR_CTAS_PER_SM")) {   // tuning aid: leave room for other kernels to co-reside
+            const int c = atoi(cap);
+            if (c >= 1 && c < per_sm) per_sm = c;
+        }
         h->lidar_grid = per_sm * sms;
     }
     // pinned staging
