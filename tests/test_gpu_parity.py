@@ -166,36 +166,40 @@ def test_pipelined_host_step_equals_device_step():
     a_env.close(); b_env.close()
 
 
-def test_full_size_shard_invariance_and_spot_check():
-    """BASELINE.json's full per-GPU size (8192 envs x 8 agents + traffic, 72 beams): (1) the job split into two
-    4096-env shards with env_id_base gives the very same bits as the single 8192-env job (size-independent
-    property: results do not depend on batching or sharding); (2) a few env ids spot-checked against the checker."""
+@pytest.mark.parametrize("E", [8192, 65536])
+def test_full_size_shard_invariance_and_spot_check(E):
+    """BASELINE.json's full size — all 65,536 envs x 8 agents + traffic, 72 beams on one GPU, and the 8192-env share of the
+    8-GPU split: (1) the job cut into two half-size shards with env_id_base gives the very same bits as the single job
+    (size-independent property: results do not depend on batching or sharding); (2) a few env ids spot-checked against
+    the checker."""
     import torch
+    H = E // 2
     base = dict(num_agents=8, num_lanes=3, ego_routes=R3[:8], traffic_flow=True, traffic_density=1.0, lidar_rays=72, seed=17,
                 auto_reset=True, max_steps=40)
-    full = _benv()(dict(base, num_envs=8192))
-    lo = _benv()(dict(base, num_envs=4096, env_id_base=0))
-    hi = _benv()(dict(base, num_envs=4096, env_id_base=4096))
-    spots = [0, 1, 4095, 4096, 8191]
+    full = _benv()(dict(base, num_envs=E))
+    lo = _benv()(dict(base, num_envs=H, env_id_base=0))
+    hi = _benv()(dict(base, num_envs=H, env_id_base=H))
+    spots = [0, 1, H - 1, H, E - 1]
     cls = checker_class()
     refs = {e: cls(num_lanes=3, ego_routes=R3[:8], traffic=True, density=1.0, lidar_rays=72, seed=17, env_id=e, max_steps=40) for e in spots}
+    spot_idx = torch.tensor(spots, device="cuda")
     for t in range(60):                       # crosses the max_steps=40 truncation -> auto-reset on every env
         full.rollout(1); lo.rollout(1); hi.rollout(1)
         torch.cuda.synchronize()
         for k in ("obs", "reward", "status", "terminated", "truncated", "lidar_hit", "npc_count", "npc_x", "ego_x", "ego_heading"):
             f = full.buf[k]
-            assert torch.equal(f[:4096], lo.buf[k]) and torch.equal(f[4096:], hi.buf[k]), (t, k)
-        obs = full.buf["obs"].cpu().numpy()
-        st = full.buf["status"].cpu().numpy()
-        for e, r in refs.items():
+            assert torch.equal(f[:H], lo.buf[k]) and torch.equal(f[H:], hi.buf[k]), (t, k)
+        obs = full.buf["obs"][spot_idx].cpu().numpy()
+        st = full.buf["status"][spot_idx].cpu().numpy()
+        for i, (e, r) in enumerate(refs.items()):
             a = po.philox_actions(17, e, r.tick + 1, 8)
             o = r.step(a)
-            assert (obs[e].view(np.uint32) == o["obs"].view(np.uint32)).all(), (t, e)
-            assert (st[e] == o["status"]).all(), (t, e)
+            assert (obs[i].view(np.uint32) == o["obs"].view(np.uint32)).all(), (t, e)
+            assert (st[i] == o["status"]).all(), (t, e)
             if o["terminated"] or o["truncated"]:
                 r.reset()                     # the stepper auto-resets at the start of its next step
     s = full.stats()
-    assert s["agent_steps"] == 8192 * 8 * 60 and s["env_resets"] == 8192 and s["npc_overflow"] == 0
+    assert s["agent_steps"] == E * 8 * 60 and s["env_resets"] == E and s["npc_overflow"] == 0
     for x in (full, lo, hi):
         x.close()
 
