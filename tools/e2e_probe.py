@@ -27,7 +27,7 @@ def bw(nbytes, d2h=True, reps=20):
 
 
 def main():
-    E, N = 8192, 8
+    E, N = (int(sys.argv[1]) if len(sys.argv) > 1 else 8192), 8
     obs_bytes = E * N * 127 * 4
     for frac in (1, 4, 8, 16):
         print(f"D2H {obs_bytes // frac / 1e6:8.2f} MB : {bw(obs_bytes // frac):6.1f} GB/s")
