@@ -385,13 +385,13 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         // range's obs rows.  Measured on B200 + PCIe gen5 (tools/e2e_probe.py): the D2H of obs is 589 us of a 729 us step
         // at 8192x8; each range costs ~55 us of fixed kernel latency, so few equal ranges beat many or geometric ones.
         // One group: 4 equal ranges, 8 from 32768 envs up where the fixed cost per range no longer shows
-        // (ISX_PIPE_PLAN="w0,w1,..." (<= 8 weights) overrides, for tuning).  Several groups:
+        // (ISX_PIPE_PLAN="w0,w1,..." (<= 16 weights) overrides, for tuning).  Several groups:
         // every group is one range.
         if (n_groups == 1) {
-            int w[8] = {1, 1, 1, 1, 1, 1, 1, 1}, nw = d.E >= 32768 ? 8 : d.E >= 1024 ? 4 : 1;   // 65536 envs: 5379 us with 4 ranges, 5118 with 8
+            int w[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, nw = d.E >= 32768 ? 8 : d.E >= 1024 ? 4 : 1;   // 65536 envs: 5379 us with 4 ranges, 5118 with 8
             if (const char* plan = getenv("ISX_PIPE_PLAN")) {
                 int k = 0;
-                for (const char* c = plan; *c && k < 8;) {
+                for (const char* c = plan; *c && k < 16;) {
                     char* endp = nullptr;
                     const long v = std::strtol(c, &endp, 10);
                     if (endp == c) break;
