@@ -199,13 +199,20 @@ class BatchedIntersectionEnv:
             self._hv["step"] = view(aux[1], (E,), C.c_int32, np.int32)
         return self._hv
 
-    def step_host(self, actions: np.ndarray, dt: float = 1.0 / 60.0, copy: bool = False):
+    @property
+    def host_actions(self) -> np.ndarray:
+        """The pinned [E, N, 2] float32 staging buffer the host step uploads from: a policy that writes its output here in
+        place (and then calls ``step_host(None)``) saves the staging copy (0.3 ms per step at 65,536 envs x 8 agents)."""
+        return self._host_views()["actions"]
+
+    def step_host(self, actions: Optional[np.ndarray], dt: float = 1.0 / 60.0, copy: bool = False):
         """The same step through HOST buffers (what env.py's list<->numpy conversions amount to): host actions in, host
         obs / reward / done / status / terminated / truncated out.  The returned arrays are views of the library's pinned
         staging buffers, overwritten by the next host step (copy=True detaches them).  Device->host copies are pipelined
         behind the kernels shard by shard (isx_step_pinned)."""
         hv = self._host_views()
-        np.copyto(hv["actions"], np.asarray(actions, dtype=np.float32).reshape(hv["actions"].shape))
+        if actions is not None:                        # None: the caller already wrote this step's actions into host_actions
+            np.copyto(hv["actions"], np.asarray(actions, dtype=np.float32).reshape(hv["actions"].shape))
         _lib.check(self._lib, self._lib.isx_step_pinned(self._h, C.c_float(dt), self._stream()))
         out = (hv["obs"], hv["reward"], hv["done"], hv["status"], hv["terminated"].astype(bool), hv["truncated"].astype(bool))
         if copy:

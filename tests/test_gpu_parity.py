@@ -155,7 +155,11 @@ def test_pipelined_host_step_equals_device_step():
             b_env.step(torch.from_numpy(act).cuda(), dt)
             act = -act
             obs_d, rew_d, term_d, trunc_d, info = a_env.step(torch.from_numpy(act).cuda(), dt)
-        obs_h, rew_h, done_h, status_h, term_h, trunc_h = b_env.step_host(act, dt)
+        if t % 2:
+            obs_h, rew_h, done_h, status_h, term_h, trunc_h = b_env.step_host(act, dt)
+        else:                                 # in-place variant: actions written straight into the pinned staging buffer
+            b_env.host_actions[...] = act
+            obs_h, rew_h, done_h, status_h, term_h, trunc_h = b_env.step_host(None, dt)
         torch.cuda.synchronize()
         assert (obs_d.cpu().numpy().view(np.uint32) == obs_h.view(np.uint32)).all(), t
         assert (rew_d.cpu().numpy().view(np.uint32) == rew_h.view(np.uint32)).all(), t
