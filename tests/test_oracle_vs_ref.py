@@ -60,6 +60,17 @@ def lockstep(kw, steps, seed, policy=None):
     (dict(num_lanes=3, ego_routes=R3[:8], traffic=True, density=1.0, lidar_rays=72), 500),
     (dict(num_lanes=2, ego_routes=po.ROUTES_2LANES[:4], traffic=True, density=3.0, respawn=False, max_steps=300), 600),
     (dict(num_lanes=3, ego_routes=[("IN_6", "OUT_2")], traffic=True, density=30.0), 800),
+    # the edge shapes the GPU suite uses, so that the C restatement is pinned on them too (it is the checker on boxes
+    # where oracle/_ref did not travel): 1 and 4 lanes, > 16 neighbours with tied distances (std::sort's introsort
+    # regime, IntersectionEnv.cpp:490), custom reward weights without respawn
+    (dict(num_lanes=1, ego_routes=[("IN_1", "OUT_3"), ("IN_2", "OUT_1")], traffic=True, density=3.0,
+          traffic_routes=[("IN_3", "OUT_1"), ("IN_4", "OUT_2")]), 400),
+    (dict(num_lanes=4, ego_routes=[("IN_1", "OUT_9"), ("IN_6", "OUT_15"), ("IN_11", "OUT_2"), ("IN_16", "OUT_4")], traffic=True, density=3.0,
+          traffic_routes=[("IN_2", "OUT_10"), ("IN_7", "OUT_13"), ("IN_12", "OUT_3"), ("IN_13", "OUT_7")]), 400),
+    (dict(num_lanes=3, ego_routes=[R3[i % 12] for i in range(20)], traffic=True, density=3.0, max_steps=120), 300),
+    (dict(num_lanes=3, ego_routes=[R3[i % 12] for i in range(32)], traffic=True, density=6.0, max_steps=120), 200),
+    (dict(num_lanes=3, ego_routes=R3[:3], respawn=False, max_steps=90, use_team=True,
+          reward=(3.0, 2.5, -0.5, -7.0, -3.0, 20.0, -0.3, 0.7)), 300),
 ])
 def test_lockstep_random_actions(kw, steps):
     lockstep(kw, steps, seed=1)
