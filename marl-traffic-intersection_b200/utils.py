@@ -6,45 +6,21 @@ is not reproduced: lane points come from the library (``isx_route`` / RouteGen.c
 
 OBS_DIM = 127
 
-DEFAULT_ROUTE_MAPPING_2LANES = {
-    "IN_1": ["OUT_3"],
-    "IN_2": ["OUT_6"],
-    "IN_3": ["OUT_5"],
-    "IN_4": ["OUT_8"],
-    "IN_6": ["OUT_2"],
-    "IN_7": ["OUT_1"],
-    "IN_8": ["OUT_4"],
-}
+def _mapping(exits):
+    """{"IN_k": ["OUT_e"]} for every entry lane k = 1.. that has a default exit e (None = no default route)."""
+    return {f"IN_{k}": [f"OUT_{e}"] for k, e in enumerate(exits, start=1) if e is not None}
 
-DEFAULT_ROUTE_MAPPING_3LANES = {
-    "IN_1": ["OUT_4"],
-    "IN_2": ["OUT_8"],
-    "IN_3": ["OUT_12"],
-    "IN_4": ["OUT_7"],
-    "IN_5": ["OUT_11"],
-    "IN_6": ["OUT_3"],
-    "IN_7": ["OUT_10"],
-    "IN_8": ["OUT_2"],
-    "IN_9": ["OUT_6"],
-    "IN_10": ["OUT_1"],
-    "IN_11": ["OUT_5"],
-    "IN_12": ["OUT_9"],
-}
 
-DEFAULT_REWARD_CONFIG = {
-    "use_team_reward": False,
-    "traffic_flow": False,
-    "reward_config": {
-        "progress_scale": 10.0,
-        "stuck_speed_threshold": 1.0,
-        "stuck_penalty": -0.01,
-        "crash_vehicle_penalty": -10.0,
-        "crash_object_penalty": -5.0,
-        "success_reward": 10.0,
-        "action_smoothness_scale": -0.02,
-        "team_alpha": 0.2,
-    },
-}
+# default exit lane of IN_1, IN_2, ... (utils.py:29-52 of the reference); insertion order = entry-lane order, which is
+# the order env.py iterates the mapping in (env.py:118-122, 138-145)
+DEFAULT_ROUTE_MAPPING_2LANES = _mapping((3, 6, 5, 8, None, 2, 1, 4))
+DEFAULT_ROUTE_MAPPING_3LANES = _mapping((4, 8, 12, 7, 11, 3, 10, 2, 6, 1, 5, 9))
+
+# env.py:41-54: reward weights in reward_vector() order
+_REWARD_KEYS = ("progress_scale", "stuck_speed_threshold", "stuck_penalty", "crash_vehicle_penalty", "crash_object_penalty",
+                "success_reward", "action_smoothness_scale", "team_alpha")
+DEFAULT_REWARD_CONFIG = {"use_team_reward": False, "traffic_flow": False,
+                         "reward_config": dict(zip(_REWARD_KEYS, (10.0, 1.0, -0.01, -10.0, -5.0, 10.0, -0.02, 0.2)))}
 
 STATUS_NAMES = ("ALIVE", "DEAD", "SUCCESS", "CRASH_WALL", "CRASH_LINE", "CRASH_CAR")
 
