@@ -1,25 +1,27 @@
 #!/usr/bin/env python
 """bench.py — agent-steps/s of the batched intersection stepper on N B200s (one process per GPU).
 
-Workload (BASELINE.json configs[4], the configuration the 1e9 target is quoted on): 65,536 envs x 8 agents + NPC
-traffic density 1.0, 72-beam lidar, 3 lanes, random actions from the on-device Philox stream, respawn on, max_steps
-2000, auto-reset.  The whole configuration fits one B200 (about 0.5 GB), so that is what ONE GPU runs; with N GPUs
-every GPU runs its own 65,536 envs (env ids rank*65536 ...) -> weak scaling, no per-step collective; the only
-collective is one NCCL all-reduce of the episode counters after the timed region.  `--envs-per-gpu 8192` gives the
-65,536-envs-over-8-GPUs split of the target statement (profiles/r01/bench_8gpu_final2.json).
+Default workload = BASELINE.json configs[4] (C5), the configuration the metric and the 1e9 target are quoted on: 65,536 envs
+x 8 agents + NPC traffic density 1.0, 72-beam lidar, 3 lanes, random actions from the on-device Philox stream, respawn on,
+max_steps 2000, auto-reset.  The whole configuration fits one B200 (about 0.6 GB), so that is what ONE GPU runs; with N GPUs
+every GPU runs its own copy (env ids rank*E ...) -> weak scaling, no per-step collective; the only collective is the
+all-reduce of the episode counters after the timed regions.  Under torchrun (N > 1) the line also carries a `strong`
+sub-record: the SAME configuration cut into N contiguous env ranges (65,536/N envs per GPU at C5 = the target statement).
+`--config C2|C3|C4|C5` selects the other BASELINE configs (C4 = 96 beams).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]              # native arm (CUDA, this repo)
-  python bench.py --impl reference [--gpus N] [--steps K] ...       # the reference's own CPU env on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C5]     # native arm (CUDA, this repo)
+  python bench.py --impl reference [--gpus N] [--steps K] ...            # the reference's own CPU env, one PROCESS per host core
 
-One JSON line on stdout (rank 0).  See the module-level comments next to each key for what is measured.
-"""
+Every timed region starts from the steady state of the episode: after the W warm-up steps the batch is pre-rolled
+(--preroll, default 400 steps: NPC population and crash/respawn mix have settled), so `value`, `roofline` and `e2e`
+describe the same state whatever --steps/--warmup are; the line carries the self-check (`consistency`).
+One JSON line on stdout (rank 0)."""
 from __future__ import annotations
 
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -32,59 +34,142 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 METRIC = "agent_steps_per_sec"
 UNIT = "agent-steps/s"
 ALGO_BYTES_PER_AGENT_STEP = 610  # 8 action + 2x40 ego state + 8 consts + 508 obs + 4 reward + 1 done + 1 status
-ENVS_PER_GPU = 65536
-N_AGENTS = 8
 DT = 1.0 / 60.0
 
-ROUTES8 = [("IN_1", "OUT_4"), ("IN_2", "OUT_8"), ("IN_3", "OUT_12"), ("IN_4", "OUT_7"),
-           ("IN_5", "OUT_11"), ("IN_6", "OUT_3"), ("IN_7", "OUT_10"), ("IN_8", "OUT_2")]
+R3 = [("IN_1", "OUT_4"), ("IN_2", "OUT_8"), ("IN_3", "OUT_12"), ("IN_4", "OUT_7"),
+      ("IN_5", "OUT_11"), ("IN_6", "OUT_3"), ("IN_7", "OUT_10"), ("IN_8", "OUT_2")]
+TEAM3 = [("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")]
+# BASELINE.json configs[0..4] as SURVEY.md §8(d) pins them down
+CONFIGS = {
+    "C1": dict(label="BASELINE configs[0] (C1): single agent IN_6->OUT_2, no traffic, 96-beam lidar (the reference's CPU-runnable case)",
+               envs=1, agents=1, routes=[("IN_6", "OUT_2")], team=False, traffic=False, density=0.0, rays=96),
+    "C2": dict(label="BASELINE configs[1] (C2): 3 agents (IN_6->OUT_2, IN_4->OUT_8, IN_5->OUT_7), team reward alpha=0.2, 96-beam lidar, 1024 envs",
+               envs=1024, agents=3, routes=TEAM3, team=True, traffic=False, density=0.0, rays=96),
+    "C3": dict(label="BASELINE configs[2] (C3): single agent IN_6->OUT_2 + NPC traffic density 0.5 (12 default routes), 96-beam lidar, 4096 envs",
+               envs=4096, agents=1, routes=[("IN_6", "OUT_2")], team=False, traffic=True, density=0.5, rays=96),
+    "C4": dict(label="BASELINE configs[3] (C4): 8 agents/env, full 96-beam lidar + OBB collision, no traffic, 16,384 envs",
+               envs=16384, agents=8, routes=R3, team=False, traffic=False, density=0.0, rays=96),
+    "C5": dict(label="BASELINE configs[4] (C5): 8 agents/env + NPC traffic density 1.0, 72-beam lidar, 65,536 envs",
+               envs=65536, agents=8, routes=R3, team=False, traffic=True, density=1.0, rays=72),
+}
 
 
-def workload_config(n_gpus, envs_per_gpu):
+def workload_config(name, n_gpus, envs_per_gpu):
+    """The `config` object of the JSON line — the SAME keys and values for the native and the reference arm."""
+    c = CONFIGS[name]
     return {
-        "workload": "BASELINE configs[4] (C5): 8 agents/env + NPC traffic density 1.0, 72-beam lidar, 3 lanes, random Philox "
-                    "actions, respawn, max_steps 2000, auto-reset; the full 65,536-env configuration on every GPU by default",
-        "envs_per_gpu": envs_per_gpu, "agents_per_env": N_AGENTS, "global_envs": envs_per_gpu * n_gpus,
-        "lidar_rays": 72, "traffic_density": 1.0, "dt": DT, "parallelism": f"env-shard x{n_gpus} (no per-step collective)",
+        "workload": c["label"] + "; 3 lanes, random Philox actions, respawn, max_steps 2000, auto-reset; the whole configuration on every GPU",
+        "config_name": name, "envs_per_gpu": envs_per_gpu, "agents_per_env": c["agents"], "global_envs": envs_per_gpu * n_gpus,
+        "lidar_rays": c["rays"], "traffic_density": c["density"], "team_reward": c["team"], "dt": DT,
+        "parallelism": f"env-shard x{n_gpus} (no per-step collective)",
         "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
     }
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_run(samples: int, warmup: int, steps_per_sample: int, threads: int):
-    """Times the reference's own CPU implementation (oracle/_ref, the unmodified C++ behind a C ABI) — or the C port
-    when _ref did not travel — with one env per host thread on the bench workload.  Returns (value, info)."""
-    import pyoracle as po
+def _ref_worker(idx, cpu, cfg_name, steps_per_sample, samples, warmup, barrier, q):
+    """One PROCESS, pinned to one host core, stepping its own env of the bench configuration through the C-ABI driver of
+    the reference's C++ (oracle/_ref) — or the C port when _ref did not travel."""
+    try:
+        if cpu is not None:
+            os.sched_setaffinity(0, {cpu})
+        import pyoracle as po
+        c = CONFIGS[cfg_name]
+        kind = "reference" if po.have_ref() else "port"
+        cls = po.RefEnv if kind == "reference" else po.OracleEnv
+        env = cls(num_lanes=3, ego_routes=c["routes"], use_team=c["team"], traffic=c["traffic"], density=c["density"] or 0.5,
+                  lidar_rays=c["rays"], seed=0, env_id=idx, max_steps=2000)
+        for _ in range(warmup):
+            env.rollout(steps_per_sample, DT)
+        barrier.wait()
+        t0 = time.monotonic()
+        agent_steps = 0
+        for _ in range(samples):
+            a, _, _ = env.rollout(steps_per_sample, DT)       # random Philox actions + reset on terminated|truncated, in C
+            agent_steps += a
+        q.put((idx, kind, agent_steps, t0, time.monotonic()))
+    except Exception as ex:  # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:  # noqa: BLE001
+            pass
+        q.put((idx, "error: " + repr(ex), 0, 0.0, 0.0))
 
-    kind = "reference" if po.have_ref() else "port"
-    cls = po.RefEnv if kind == "reference" else po.OracleEnv
-    envs = [cls(num_lanes=3, ego_routes=ROUTES8, traffic=True, density=1.0, lidar_rays=72, seed=0, env_id=i, max_steps=2000)
-            for i in range(threads)]
-    done_steps = [0] * threads
 
-    def work(i, n):
-        a, _, _ = envs[i].rollout(n, DT)
-        done_steps[i] = a
+def _envpy_worker(idx, cpu, cfg_name, steps, barrier, q):
+    """The same, through the reference's own env.py over its pybind11 module MARLEnv (list<->numpy conversions included)."""
+    try:
+        if cpu is not None:
+            os.sched_setaffinity(0, {cpu})
+        import numpy as np
+        import refpy_util as R
+        c = CONFIGS[cfg_name]
+        cfg = dict(num_agents=c["agents"], ego_routes=c["routes"], use_team_reward=c["team"], traffic_flow=c["traffic"], traffic_density=c["density"] or 0.5)
+        env = R.load_reference_env("MARLEnv").IntersectionEnv(cfg)
+        rng = np.random.default_rng(idx)
+        n = 1 if c["traffic"] else c["agents"]
+        acts = rng.uniform(-1, 1, (256, n, 2)).astype(np.float32)
+        R.marlenv_seed(0, idx, 0)
+        for i in range(50):
+            env.step(acts[i][0] if c["traffic"] else acts[i])
+        barrier.wait()
+        t0 = time.monotonic()
+        for i in range(steps):
+            _, _, term, trunc, _ = env.step(acts[i & 255][0] if c["traffic"] else acts[i & 255])
+            if term or trunc:
+                env.reset()
+        q.put((idx, "env.py", steps * n, t0, time.monotonic()))
+    except Exception as ex:  # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:  # noqa: BLE001
+            pass
+        q.put((idx, "error: " + repr(ex), 0, 0.0, 0.0))
 
-    def one_sample(n):
-        ts = [threading.Thread(target=work, args=(i, n)) for i in range(threads)]
-        t0 = time.perf_counter()
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        return time.perf_counter() - t0, sum(done_steps)
 
-    for _ in range(warmup):
-        one_sample(steps_per_sample)
-    tot_t, tot_a = 0.0, 0
-    for _ in range(samples):
-        dt_, a = one_sample(steps_per_sample)
-        tot_t += dt_
-        tot_a += a
-    info = {"kind": kind, "cores": threads,
-            "sample": f"{threads} envs (one per host thread) x {steps_per_sample} env-steps x {samples} samples of the bench workload"}
-    return tot_a / tot_t, tot_t / max(samples, 1), info
+def _run_procs(target, extra_args, cpus):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")          # the parent may hold a CUDA context: never fork it
+    n = len(cpus)
+    barrier, q = ctx.Barrier(n), ctx.Queue()
+    procs = [ctx.Process(target=target, args=(i, cpus[i]) + tuple(extra_args) + (barrier, q)) for i in range(n)]
+    for p in procs:
+        p.start()
+    res, deadline = [], time.monotonic() + 900
+    while len(res) < n:
+        try:
+            res.append(q.get(timeout=2))
+        except Exception:  # noqa: BLE001  (queue.Empty)
+            if time.monotonic() > deadline or (not any(p.is_alive() for p in procs) and q.empty()):
+                for p in procs:
+                    p.kill()
+                raise RuntimeError(f"CPU baseline workers died or timed out ({len(res)} of {n} reported)")
+    for p in procs:
+        p.join(timeout=60)
+    bad = [r[1] for r in res if str(r[1]).startswith("error")]
+    if bad:
+        raise RuntimeError(bad[0])
+    total = sum(r[2] for r in res)
+    wall = max(r[4] for r in res) - min(r[3] for r in res)
+    return total / wall, wall, res[0][1]
+
+
+def cpu_reference_run(cfg_name: str, samples: int, warmup: int, steps_per_sample: int):
+    """The reference's own CPU implementation of the path on every host core this process may use: one process per core,
+    one env per process (per-env CPU cost does not depend on how many envs a job has).  Returns (value, seconds, info)."""
+    cpus = sorted(os.sched_getaffinity(0))
+    value, wall, kind = _run_procs(_ref_worker, (cfg_name, steps_per_sample, samples, warmup), cpus)
+    info = {"kind": kind, "cores": len(cpus), "processes": len(cpus),
+            "sample": f"{len(cpus)} processes (one per host core, one env of {cfg_name} each, NOT the full {CONFIGS[cfg_name]['envs']} envs: "
+                      f"per-env CPU cost is size-independent) x {steps_per_sample} env-steps x {samples} samples, through the C-ABI driver of the reference's C++"}
+    return value, wall, info
+
+
+def cpu_envpy_run(cfg_name: str, steps: int):
+    cpus = sorted(os.sched_getaffinity(0))
+    value, wall, _ = _run_procs(_envpy_worker, (cfg_name, steps), cpus)
+    return {"value": value, "unit": UNIT, "cores": len(cpus), "kind": "reference env.py over its pybind11 module MARLEnv",
+            "sample": f"{len(cpus)} processes x {steps} env.step() calls of {cfg_name}"}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -157,8 +242,9 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------- main
 def bind_to_gpu_numa_node(gpu_index: int) -> str:
     """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of
-    the host-buffer step (and the numpy copies into them) live on the GPU's own NUMA node.  Best effort: returns a short
-    description for the JSON line, never raises."""
+    the host-buffer step (and the host threads that expand them) live on the GPU's own NUMA node.  With several ranks on
+    one node the GPU-local set is additionally cut into disjoint per-rank slices.  Best effort: returns a short description
+    for the JSON line, never raises."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -175,30 +261,46 @@ def bind_to_gpu_numa_node(gpu_index: int) -> str:
         return f"unbound ({type(e).__name__})"
 
 
+def make_env(cfg_name, E, rank_base, dev):
+    from marl_traffic_intersection_b200 import BatchedIntersectionEnv
+    c = CONFIGS[cfg_name]
+    return BatchedIntersectionEnv({
+        "num_envs": E, "num_agents": c["agents"], "num_lanes": 3, "ego_routes": c["routes"], "use_team_reward": c["team"],
+        "traffic_flow": c["traffic"], "traffic_density": c["density"] or 0.5, "lidar_rays": c["rays"], "respawn_enabled": True,
+        "max_steps": 2000, "auto_reset": 1, "seed": 0, "env_id_base": rank_base, "npc_capacity": 16, "device": dev,
+    })
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--config", default="C5", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the whole configuration on every GPU")
+    ap.add_argument("--preroll", type=int, default=400, help="steps run before the timed regions (steady state of the episode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, world)
     K, W = max(1, args.steps), max(3, args.warmup)
+    cfg_name = args.config
+    cfg = CONFIGS[cfg_name]
+    E = args.envs_per_gpu or cfg["envs"]
+    N_AGENTS = cfg["agents"]
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = os.cpu_count() or 1
-        sps = max(1, min(500, 15000 // K))     # ~30 s of CPU work in total whatever K the driver asks for
-        value, s_per_step, info = cpu_reference_run(samples=K, warmup=min(W, 3), steps_per_sample=sps, threads=threads)
+        sps = max(1, min(500, 12000 // K))     # ~20-30 s of CPU work in total whatever K the driver asks for
+        value, wall, info = cpu_reference_run(cfg_name, samples=K, warmup=min(W, 3), steps_per_sample=sps)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
-                "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(n_gpus, args.envs_per_gpu),
+                "ms_per_step": wall / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(cfg_name, n_gpus, E),
                 "cpu_baseline": dict(info, value=value, unit=UNIT),
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -218,15 +320,14 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # disjoint per-rank CPU slices of whatever set the ranks share (the host expander threads of the e2e path)
+        mine = sorted(os.sched_getaffinity(0))
+        if len(mine) >= 2 * world:
+            per = len(mine) // world
+            os.sched_setaffinity(0, mine[local_rank * per:(local_rank + 1) * per])
+            cpu_binding += f"; rank slice of {per} CPUs"
 
-    from marl_traffic_intersection_b200 import BatchedIntersectionEnv
-
-    E = args.envs_per_gpu
-    env = BatchedIntersectionEnv({
-        "num_envs": E, "num_agents": N_AGENTS, "num_lanes": 3, "ego_routes": ROUTES8, "traffic_flow": True, "traffic_density": 1.0,
-        "lidar_rays": 72, "respawn_enabled": True, "max_steps": 2000, "auto_reset": True, "seed": 0, "env_id_base": rank * E,
-        "npc_capacity": 16, "device": dev,
-    })
+    env = make_env(cfg_name, E, rank * E, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -235,36 +336,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- warm-up
+    def timed_rollout(e, steps):
+        """K steps, one CUDA-event pair per step on the launching stream, L2 flushed between steps; max over ranks."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            flush.zero_()                      # evict L2 between timed steps (outside the event pair)
+            ev[i][0].record()
+            e.rollout(1)                       # k_traffic (if any), k_ego, k_features, k_lidar_obs
+            ev[i][1].record()
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- warm-up, then pre-roll into the steady state of the episode
     env.rollout(W)
+    env.rollout(max(0, args.preroll))
     barrier()
 
-    # ---------------- timed region 1: device-resident rollout, K steps, CUDA events on the launching stream
+    # ---------------- timed region 1: device-resident rollout, K steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
     t_wall0 = time.perf_counter()
-    for i in range(K):
-        flush.zero_()                      # evict L2 between timed steps (outside the event pair)
-        ev[i][0].record()
-        env.rollout(1)                     # 4 kernel launches: k_traffic, k_ego, k_features, k_lidar_obs
-        ev[i][1].record()
-    barrier()
+    ms_max = timed_rollout(env, K)
     t_wall = time.perf_counter() - t_wall0
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    agent_steps_total = E * N_AGENTS * K * world
-    value = agent_steps_total / (ms_max * 1e-3)
+    value = E * N_AGENTS * K * world / (ms_max * 1e-3)
+    launches_per_step = 4 if cfg["traffic"] else 3
 
-    # ---------------- per-kernel time for the roofline line (CUDA events around each launch, live)
+    # ---------------- per-kernel time for the roofline line (CUDA events around each launch, live, same state)
     kr = min(K, 200)
-    env.rollout(300)                                # mid-episode state, so the per-kernel times are representative
-    ms4 = env.rollout_timed4(kr)                    # CUDA events around every launch, on the launching stream
+    ms4 = env.rollout_timed4(kr)
     us4 = [1e3 * x / kr for x in ms4]
     lid_s = us4[3] * 1e-6                           # dominant kernel: k_lidar_obs
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -273,20 +377,26 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback"
     achieved = ALGO_BYTES_PER_AGENT_STEP * E * N_AGENTS / lid_s / 1e9
-    traffic = None
-    rp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    ncu = {}
+    rp = os.path.join(ROOT, "profiles", "roofline_ncu.json")     # numbers read off the committed ncu captures, per config and env count
     if os.path.exists(rp):
         try:
-            traffic = json.load(open(rp)).get("k_lidar_obs_dram_bytes_per_launch", {}).get(str(E))   # measured per env count
+            ncu = json.load(open(rp)).get(f"{cfg_name}:{E}", {})
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_lidar_obs", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "us_per_launch": us4[3],
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_AGENT_STEP * E * N_AGENTS,
+            ncu = {}
+    step_us = 1e3 * ms_max / K
+    roofline = {"bound": "hbm", "binding_limit": "issue slots (see `issue`)", "kernel": "k_lidar_obs", "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu.get("dram_bytes_per_launch"),
+                "us_per_launch": us4[3], "algorithmic_bytes_per_launch": ALGO_BYTES_PER_AGENT_STEP * E * N_AGENTS,
                 "all_kernels_us_per_launch": {"k_traffic": us4[0], "k_ego": us4[1], "k_features": us4[2], "k_lidar_obs": us4[3]},
-                "note": "the path is instruction-issue-bound, not HBM-bound (SURVEY.md 8d predicted ~1% of the HBM roofline at the "
-                        "target rate): k_lidar_obs issues 0.86 warp-instructions/cycle/SMSP of a possible 1.0 with the ALU pipe "
-                        "at 70% (profiles/r01); its DRAM traffic is 0.91x the algorithmic bytes, i.e. no wasted re-reads"}
+                "issue": ncu.get("issue"),
+                "note": "the path is instruction-issue-bound, not HBM-bound (SURVEY.md 8d predicted ~1% of the HBM roofline at the target "
+                        "rate); `issue` = warp-instructions issued per cycle per SM sub-partition (ceiling 1.0) and the mean active lanes "
+                        "per instruction (ceiling 32) of the dominant kernel, from the committed ncu capture of this configuration"}
+    consistency = {"step_us": step_us, "sum_kernels_us": sum(us4), "dominant_kernel_us": us4[3],
+                   "sum_kernels_over_step": sum(us4) / step_us, "ok": bool(us4[3] <= step_us * 1.02 and sum(us4) <= step_us * 1.05),
+                   "note": "per-kernel times are taken right after the timed region in the same episode state, with an event between "
+                           "launches (no programmatic overlap), so their sum may exceed the step by a few per cent but never by more"}
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers
     Ke = min(K, 100)
@@ -297,47 +407,80 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for i in range(Ke):
-        env.step_host(acts[i % 4], DT)     # H2D actions, 2 kernels, D2H obs/reward/done/status/terminated/truncated, sync
+        env.step_host(acts[i % 4], DT)     # H2D actions, step kernels, D2H of the step's results, host obs rows complete, sync
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = E * N_AGENTS * Ke * world / float(te.item())
-    h2d = E * N_AGENTS * 2 * 4
-    d2h = E * N_AGENTS * (127 * 4 + 4 + 1 + 1) + 2 * E + 2 * 4 * E     # obs, reward, done, status; terminated, truncated; agents_alive, step
+    io = env.host_step_bytes() if hasattr(env, "host_step_bytes") else None
+    if io is None:
+        io = {"h2d": E * N_AGENTS * 2 * 4, "d2h": E * N_AGENTS * (127 * 4 + 4 + 1 + 1) + 2 * E + 2 * 4 * E}
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"], "steps": Ke,
+           "ms_per_step": 1e3 * float(te.item()) / Ke, "d2h_gb_per_s_per_rank": io["d2h"] * Ke / float(te.item()) / 1e9}
+    for k in ("host_expand_threads", "obs_transport"):
+        if k in io:
+            e2e[k] = io[k]
 
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---------------- the one collective: all-reduce(sum) of the episode counters
-    st = env.stats_tensor().clone()
-    if world > 1:
-        counters = st.clone()
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
-    else:
-        counters = st
-    counters = counters.cpu().tolist()
-    stats = {"agent_steps": counters[11], "status_hist": counters[0:6], "npc_spawned": counters[6], "npc_removed": counters[7],
-             "npc_collided": counters[8], "npc_overflow": counters[9], "env_resets": counters[10], "neighbor_tie_sorts": counters[12]}
+    # ---------------- strong-scaling sub-record: the same configuration cut into `world` env ranges
+    strong = None
+    if world > 1 and not args.no_strong and cfg["envs"] % world == 0:
+        Es = cfg["envs"] // world
+        env_s = make_env(cfg_name, Es, rank * Es, dev)
+        env_s.rollout(W)
+        env_s.rollout(max(0, args.preroll))
+        ms_s = timed_rollout(env_s, K)
+        strong = {"scaling": "strong", "global_envs": cfg["envs"], "envs_per_gpu": Es, "value": cfg["envs"] * N_AGENTS * K / (ms_s * 1e-3),
+                  "unit": UNIT, "ms_per_step": ms_s / K, "steps": K,
+                  "note": "BASELINE target statement: the configuration's env count split over the GPUs (contiguous env-id ranges)"}
+        env_s.close()
 
-    cpu_baseline = None
+    # ---------------- the one collective: all-reduce(sum) of the episode counters (int64[15]) and of reward_sum (float64[1])
+    stats = env.reduce_stats()
+
+    cpu_baseline = cpu_env_py = facade = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # single-env latency of the reference-compatible facade (BASELINE configs[0]: E = 1 is latency-, not throughput-bound)
+        try:
+            from marl_traffic_intersection_b200 import IntersectionEnv
+            fe = IntersectionEnv({"num_agents": 1, "ego_routes": [("IN_6", "OUT_2")]})
+            a1 = np.array([0.3, 0.1], np.float32)
+            for _ in range(50):
+                fe.step(a1)
+            t0 = time.perf_counter()
+            for _ in range(300):
+                _, _, tm, tr, _ = fe.step(a1)
+                if tm or tr:
+                    fe.reset()
+            facade = {"config": "C1 through the env.py-compatible facade, E = 1", "us_per_step": (time.perf_counter() - t0) / 300 * 1e6,
+                      "note": "one env on a GPU is launch-latency-bound; the reference's CPU env.py takes 40-70 us per step here (cpu_env_py.C1)"}
+            fe.close()
+        except Exception as ex:  # noqa: BLE001
+            facade = {"error": repr(ex)}
         os.sched_setaffinity(0, all_cpus)               # the CPU baseline gets every host core again
         try:
-            threads = os.cpu_count() or 1
-            v, _, info = cpu_reference_run(samples=10, warmup=1, steps_per_sample=400, threads=threads)
+            v, _, info = cpu_reference_run(cfg_name, samples=8, warmup=1, steps_per_sample=400)
             cpu_baseline = dict(info, value=v, unit=UNIT)
         except Exception as ex:  # the checker libraries did not travel: report, do not fail the bench
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+        try:
+            import refpy_util
+            if refpy_util.have_pyref():
+                cpu_env_py = {c: cpu_envpy_run(c, 4000) for c in ("C1", "C2", "C3")}
+        except Exception as ex:  # noqa: BLE001
+            cpu_env_py = {"error": repr(ex)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(workload_config(world, E), host_cpu_binding=cpu_binding),
-            "clocks": clocks, "gpu_launches": 4 * K,   # k_traffic, k_ego, k_features, k_lidar_obs per step
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "stats": stats, "wall_s_timed_region": t_wall,
-            "target_1e9_frac": value / 1e9,
+            "data": "synthetic", "config": workload_config(cfg_name, world, E), "host_cpu_binding": cpu_binding,
+            "preroll_steps": args.preroll, "clocks": clocks, "gpu_launches": launches_per_step * K,
+            "e2e": e2e, "roofline": roofline, "consistency": consistency, "strong": strong,
+            "cpu_baseline": cpu_baseline, "cpu_env_py": cpu_env_py, "single_env_facade": facade,
+            "stats": stats, "wall_s_timed_region": t_wall, "target_1e9_frac": value / 1e9,
         }
         print(json.dumps(line), flush=True)
     env.close()

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ISX_ABI_VERSION 1
+#define ISX_ABI_VERSION 2
 #define ISX_OBS_DIM 127          /* IntersectionEnv.cpp:424 : 6 ego + 5x5 neighbours + 96 lidar */
 #define ISX_PATH_LEN 160         /* RouteGen.cpp:111-205: 50 + 60 + 50 way-points */
 #define ISX_MAX_AGENTS 32        /* egos per env */
@@ -61,7 +61,14 @@ typedef struct isx_config {
     const char *const *traffic_end;
     uint64_t seed;               /* Philox key (the reference is unseedable, TrafficFlow.cpp:278,324) */
     int64_t env_id_base;         /* global id of local env 0 */
-    int32_t auto_reset;          /* isx_rollout / isx_step: reset an env at the start of the step after terminated|truncated */
+    int32_t auto_reset;          /* The reference has no auto-reset: a caller of env.py resets after terminated|truncated.
+                                  * 0 = the same here (isx_reset with a mask).
+                                  * 1 = the env is reset at the START of the step that follows a terminated|truncated step, and that
+                                  *     step's action already drives the new episode (it was chosen from the terminal observation;
+                                  *     the reset observation itself is never returned).  What isx_rollout's random-action benchmark uses.
+                                  * 2 = next-step reset as Gymnasium's vector envs do it: the call after a terminated|truncated step only
+                                  *     resets — action ignored, nothing simulated (step 0, RNG tick unchanged), reward 0, done 0,
+                                  *     terminated = truncated = 0, and obs is what reset() returns (lidar part 1.0). */
     int32_t reserved;
 } isx_config;
 
@@ -203,6 +210,27 @@ int isx_snapshot_save(isx_handle *h, isx_snapshot *s, void *stream);
 int isx_snapshot_restore(isx_handle *h, isx_snapshot *s, const uint8_t *env_mask_dev, void *stream);
 int isx_snapshot_destroy(isx_snapshot *s);
 
+/* Beam count of the handle's lidars at run time (Lidar.h:11-14: `rays` is a field of each Lidar object; the reference
+ * swaps the objects — add_car_with_route builds 96-beam lidars, IntersectionEnv.cpp:112-128, set_state leaves default
+ * 72-beam ones behind, :411-415).  Clears every stored hit (a fresh Lidar reads 250 px on all beams), zeroes the obs
+ * columns beyond the new count and refreshes the observation.  Synchronous. */
+int isx_set_lidar_rays(isx_handle *h, int32_t rays);
+int isx_lidar_rays(isx_handle *h);
+
+/* What a caller may change on a live reference env: reward_config.* (def_readwrite, bindings.cpp:33-42,63), configure() and
+ * configure_traffic()'s density (IntersectionEnv.cpp:50-60).  group = config group of a heterogeneous batch, < 0 = all.
+ * Effective from the next step; no buffers are rebuilt.  (Routes, agent count and traffic on/off shape the buffers: those
+ * need a new handle.) */
+int isx_set_reward(isx_handle *h, int32_t group, const float *k8);
+int isx_configure_episode(isx_handle *h, int32_t group, int32_t use_team, int32_t respawn, int32_t max_steps);
+int isx_set_traffic_density(isx_handle *h, int32_t group, float density);
+
+/* Car.update(throttle, steer_input, dt) / Car.check_collision(other) of bindings.cpp:30-31 for detached car records,
+ * evaluated on the GPU by the very device functions the step kernels use (Car.cpp:9-40, 105-141; 54x24 px cars).
+ * isx_car_update rewrites x, y, v, heading, acc, steer of *car in place.  Synchronous, unit-level (not a fast path). */
+int isx_car_update(int32_t device, isx_car_state *car, float throttle, float steer_input, float dt);
+int isx_car_check_collision(int32_t device, const isx_car_state *a, const isx_car_state *b, int32_t *collide);
+
 /* get_observations() (IntersectionEnv.cpp:418-520) for the current state, without stepping. */
 int isx_observe(isx_handle *h, void *stream);
 
@@ -220,8 +248,14 @@ int isx_trace_read(isx_handle *h, long long *out16_per_env);
 /* Tuning aid: one host-buffer step (stream path) with CUDA events around every pipeline range; ms[4*i+0..3] = kernels
  * begin / kernels end / copy begin / copy end of range i, ms since the step began.  Returns the number of ranges. */
 int isx_pipe_timeline(isx_handle *h, float dt, void *stream, float *ms, int32_t cap_ranges);
-/* device pointer to the raw counters (int64[16], reward_sum as double in slot 15) for an NCCL all-reduce */
-int isx_stats_device_ptr(isx_handle *h, void **ptr, int32_t *n_int64);
+/* Device pointers for the one collective this path has: the reduced episode counters as int64[ISX_STATS_COUNTERS]
+ * (indices ISX_STAT_*; integers only, so an all-reduce(sum) over int64 is exact) and, SEPARATELY, reward_sum as float64[1]
+ * (all-reduce it as a double: a double's bit pattern must never ride in an integer sum).  Reduces the per-env counters on
+ * `stream` and synchronises it; the pointers stay valid until isx_destroy and are refreshed by every call. */
+#define ISX_STATS_COUNTERS 15
+enum { ISX_STAT_HIST0 = 0, ISX_STAT_SPAWNED = 6, ISX_STAT_REMOVED = 7, ISX_STAT_COLLIDED = 8, ISX_STAT_OVERFLOW = 9,
+       ISX_STAT_RESETS = 10, ISX_STAT_AGENT_STEPS = 11, ISX_STAT_TIE_SORTS = 12 };
+int isx_stats_device_ptrs(isx_handle *h, void **counters_i64, int32_t *n_counters, void **reward_sum_f64, void *stream);
 
 /* Host-side route table probe (RouteGen.cpp:7-205 restated in the library): returns the path length,
  * ISX_E_ROUTE_START / ISX_E_ROUTE_END for unknown ids.  path_xy = 320 floats. */

@@ -8,9 +8,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ISX_LIB") or os.path.join(HERE, "csrc", "libisx_b200.so")   # ISX_LIB: tuning builds (tools/)
 
-ISX_ABI_VERSION = 1
+ISX_ABI_VERSION = 2
 OBS_DIM = 127
 MAX_RAYS = 96
+STATS_COUNTERS = 15          # isx.h ISX_STATS_COUNTERS; indices ISX_STAT_*
+STAT_INDEX = {"npc_spawned": 6, "npc_removed": 7, "npc_collided": 8, "npc_overflow": 9,
+              "env_resets": 10, "agent_steps": 11, "neighbor_tie_sorts": 12}
 E_ARG, E_CUDA, E_ROUTE_START, E_ROUTE_END, E_STATE = -1, -2, -3, -4, -5
 
 
@@ -73,7 +76,9 @@ EXPORTS = [
     "isx_step_pinned", "isx_host_views", "isx_host_views_aux",
     "isx_rollout", "isx_rollout_timed", "isx_rollout_timed4", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
     "isx_observe", "isx_render", "isx_snapshot_create", "isx_snapshot_save", "isx_snapshot_restore", "isx_snapshot_destroy",
-    "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_pipe_timeline", "isx_stats_device_ptr", "isx_route", "isx_math_probe",
+    "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_pipe_timeline", "isx_stats_device_ptrs", "isx_route", "isx_math_probe",
+    "isx_set_lidar_rays", "isx_lidar_rays", "isx_set_reward", "isx_configure_episode", "isx_set_traffic_density",
+    "isx_car_update", "isx_car_check_collision",
 ]
 
 _lib = None
@@ -124,7 +129,14 @@ def load_library(path: str | None = None):
     lib.isx_stats_reset.argtypes = [vp]
     lib.isx_trace_read.argtypes = [vp, vp]
     lib.isx_pipe_timeline.argtypes = [vp, f32, vp, C.POINTER(f32), i32]
-    lib.isx_stats_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
+    lib.isx_stats_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), vp]
+    lib.isx_set_lidar_rays.argtypes = [vp, i32]
+    lib.isx_lidar_rays.argtypes = [vp]
+    lib.isx_set_reward.argtypes = [vp, i32, C.POINTER(f32)]
+    lib.isx_configure_episode.argtypes = [vp, i32, i32, i32, i32]
+    lib.isx_set_traffic_density.argtypes = [vp, i32, f32]
+    lib.isx_car_update.argtypes = [i32, C.POINTER(CarState), f32, f32, f32]
+    lib.isx_car_check_collision.argtypes = [i32, C.POINTER(CarState), C.POINTER(CarState), C.POINTER(i32)]
     lib.isx_route.argtypes = [i32, C.c_char_p, C.c_char_p, vp, C.POINTER(i32), C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]
     lib.isx_math_probe.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     for n in EXPORTS:

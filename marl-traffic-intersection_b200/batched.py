@@ -35,10 +35,33 @@ def _strarr(items: Sequence[str]):
     return arr
 
 
+def reduce_stat_tensors(counters: torch.Tensor, reward_sum: torch.Tensor, group=None) -> Dict[str, Any]:
+    """all-reduce(sum) of the int64[15] counter vector and — separately, as a double — of reward_sum[1] over the ranks of
+    `group` (torch.distributed: NCCL for device tensors, gloo for host tensors), then the named totals.  Reduces IN PLACE.
+    Without an initialised process group the local values are returned."""
+    import torch.distributed as dist
+    if counters.dtype != torch.int64 or reward_sum.dtype != torch.float64:
+        raise TypeError("counters must be int64 and reward_sum float64 (a double's bit pattern must not ride in an integer sum)")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(reward_sum, op=dist.ReduceOp.SUM, group=group)
+    c = counters.cpu().tolist()
+    out = {k: c[i] for k, i in _lib.STAT_INDEX.items()}
+    out["status_hist"] = {STATUS_NAMES[i]: c[i] for i in range(6)}
+    out["reward_sum"] = float(reward_sum.cpu()[0])
+    return out
+
+
 class BatchedIntersectionEnv:
     """config keys (all optional): num_envs, num_agents, num_lanes, ego_routes, use_team_reward,
     respawn_enabled, max_steps, traffic_flow, traffic_density, traffic_routes, reward_config, lidar_rays (96|72),
     npc_capacity, seed, device, env_id_base, auto_reset.
+
+    ``auto_reset`` (the reference has none; a caller of env.py resets after terminated|truncated): 0/False = call
+    ``reset(mask)`` yourself; 1/True = the env is reset at the START of the step after a terminated|truncated step and that
+    step's action already drives the new episode (the policy chose it from the terminal observation; the reset observation
+    is never returned) — what the random-action benchmark uses; 2 = next-step reset as in Gymnasium's vector envs: the call
+    after a terminated|truncated step only resets (action ignored, reward 0, flags 0) and returns the reset observation.
 
     ``config`` may also be a LIST of such dicts: a heterogeneous batch whose env range is the concatenation of the
     groups (isx_create_groups) — routes, lane count, traffic, reward weights and episode settings per group, one set of
@@ -121,7 +144,7 @@ class BatchedIntersectionEnv:
         c.traffic_start, c.traffic_end = keep[2], keep[3]
         c.seed = int(cfg.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
         c.env_id_base = int(cfg.get("env_id_base", 0))
-        c.auto_reset = int(bool(cfg.get("auto_reset", False)))
+        c.auto_reset = int(cfg.get("auto_reset", 0))          # 0 off, 1/True reset-and-act, 2 next-step reset (isx.h)
         return dict(num_envs=c.num_envs, num_agents=num_agents, num_lanes=num_lanes, lidar_rays=c.lidar_rays,
                     max_steps=c.max_steps, ego_routes=routes, traffic_routes=troutes, traffic_flow=bool(c.traffic_flow),
                     npc_capacity=c.npc_capacity if c.npc_capacity > 0 else 16)
@@ -235,6 +258,28 @@ class BatchedIntersectionEnv:
         _lib.check(self._lib, self._lib.isx_rollout_timed4(self._h, int(steps), C.c_float(dt), self._stream(), ms))
         return tuple(ms)
 
+    # ------------------------------------------------------------------ run-time settings (no buffers are rebuilt)
+    def set_lidar_rays(self, rays: int):
+        """Beam count of every lidar (Lidar.rays, Lidar.h:11): clears the stored hits and refreshes obs."""
+        _lib.check(self._lib, self._lib.isx_set_lidar_rays(self._h, int(rays)))
+        self.lidar_rays = int(rays)
+        for gc in self.group_configs:
+            gc["lidar_rays"] = int(rays)
+
+    def set_reward_config(self, reward_cfg=None, group: int = -1):
+        """reward_config.* of the reference env object (bindings.cpp:33-42); dict with env.py's keys or an 8-vector."""
+        vec = reward_vector(reward_cfg) if (reward_cfg is None or isinstance(reward_cfg, dict)) else tuple(float(x) for x in reward_cfg)
+        _lib.check(self._lib, self._lib.isx_set_reward(self._h, int(group), (C.c_float * 8)(*vec)))
+
+    def configure(self, use_team: bool, respawn: bool, max_steps: int, group: int = -1):
+        """IntersectionEnv.configure(use_team, respawn, max_steps) (IntersectionEnv.cpp:50-54) on the live batch."""
+        _lib.check(self._lib, self._lib.isx_configure_episode(self._h, int(group), int(bool(use_team)), int(bool(respawn)), int(max_steps)))
+        if group < 0:
+            self.max_steps = int(max_steps)
+
+    def set_traffic_density(self, density: float, group: int = -1):
+        _lib.check(self._lib, self._lib.isx_set_traffic_density(self._h, int(group), C.c_float(max(0.0, float(density)))))
+
     def observe(self):
         _lib.check(self._lib, self._lib.isx_observe(self._h, self._stream()))
         return self.buf["obs"]
@@ -275,11 +320,18 @@ class BatchedIntersectionEnv:
                 "npc_overflow": s.npc_overflow, "env_resets": s.env_resets, "reward_sum": s.reward_sum,
                 "neighbor_tie_sorts": s.neighbor_tie_sorts}
 
-    def stats_tensor(self) -> torch.Tensor:
-        """int64[16] device view of the reduced counters (slot 15 = reward_sum bits) for an NCCL all-reduce."""
-        p, n = C.c_void_p(), C.c_int32()
-        _lib.check(self._lib, self._lib.isx_stats_device_ptr(self._h, C.byref(p), C.byref(n)))
-        return torch.as_tensor(_DevArray(p.value, (n.value,), "i8", self), device=self.device)
+    def stats_tensors(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device views for the one collective of this path: (int64[15] counters, float64[1] reward_sum).  They are two
+        tensors on purpose — all-reduce(sum) the counters as integers and reward_sum as a double (`reduce_stats` does)."""
+        p, r, n = C.c_void_p(), C.c_void_p(), C.c_int32()
+        _lib.check(self._lib, self._lib.isx_stats_device_ptrs(self._h, C.byref(p), C.byref(n), C.byref(r), self._stream()))
+        return (torch.as_tensor(_DevArray(p.value, (n.value,), "i8", self), device=self.device),
+                torch.as_tensor(_DevArray(r.value, (1,), "f8", self), device=self.device))
+
+    def reduce_stats(self, group=None) -> Dict[str, Any]:
+        """Job totals of the episode counters over the ranks of `group`: the only collective the path has."""
+        cnt, rs = self.stats_tensors()
+        return reduce_stat_tensors(cnt.clone(), rs.clone(), group)
 
     def reset_stats(self):
         _lib.check(self._lib, self._lib.isx_stats_reset(self._h))

@@ -29,6 +29,7 @@ cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st
 cudaError_t launch_render(const Dev& d, int env, uint8_t* rgb, cudaStream_t st);
 cudaError_t launch_snapshot_restore(const void* tab, int n_arrays, const uint8_t* mask, int E, cudaStream_t st);
 cudaError_t launch_math_probe(int n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr, cudaStream_t st);
+cudaError_t launch_car_unit(int op, float* io6, const float* other3, float thr, float st, float dt, int* flag, cudaStream_t st_);
 cudaError_t lidar_set_smem_attr(const Dev& d);
 cudaError_t lidar_occupancy(const Dev& d, int* ctas_per_sm);
 }  // namespace isx
@@ -97,6 +98,7 @@ static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
     s.obs += oEN * ISX_OBS_DIM; s.reward += oEN; s.done += oEN; s.status += oEN;
     s.terminated += oE; s.truncated += oE; s.agents_alive += oE; s.lidar_hit += oEN * ISX_MAX_RAYS;
     s.events += oE; s.env_stats += oE * STAT_SLOTS;
+    if (d.trace) s.trace = d.trace + oE * 16;
     return s;
 }
 
@@ -180,12 +182,13 @@ static int config_to_dev(const isx_config* cfg, Dev& d) {
     if (cfg->num_lanes < 1 || cfg->num_lanes > 4) return fail(ISX_E_ARG, "num_lanes must be in [1,4]");
     if (cfg->lidar_rays < 1 || cfg->lidar_rays > ISX_MAX_RAYS) return fail(ISX_E_ARG, "lidar_rays must be in [1,%d]", ISX_MAX_RAYS);
     if (cfg->npc_capacity < 0 || cfg->npc_capacity > ISX_MAX_NPC) return fail(ISX_E_ARG, "npc_capacity must be in [0,%d]", ISX_MAX_NPC);
+    if (cfg->auto_reset < 0 || cfg->auto_reset > 2) return fail(ISX_E_ARG, "auto_reset must be 0, 1 or 2");
     if (cfg->num_traffic_routes < 0 || cfg->num_traffic_routes > ISX_MAX_ROUTES) return fail(ISX_E_ARG, "num_traffic_routes must be in [0,%d]", ISX_MAX_ROUTES);
     if (!cfg->ego_start || !cfg->ego_end) return fail(ISX_E_ARG, "ego routes missing");
     d.E = cfg->num_envs; d.N = cfg->num_agents; d.M = cfg->traffic_flow ? (cfg->npc_capacity > 0 ? cfg->npc_capacity : 16) : 1;
     d.R = cfg->lidar_rays; d.lanes = cfg->num_lanes;
     d.use_team = cfg->use_team_reward != 0; d.respawn = cfg->respawn_enabled != 0; d.max_steps = cfg->max_steps;
-    d.traffic = cfg->traffic_flow != 0; d.T = cfg->num_traffic_routes; d.auto_reset = cfg->auto_reset != 0;
+    d.traffic = cfg->traffic_flow != 0; d.T = cfg->num_traffic_routes; d.auto_reset = cfg->auto_reset;
     d.rc = RewardCfg{cfg->reward[0], cfg->reward[1], cfg->reward[2], cfg->reward[3], cfg->reward[4], cfg->reward[5], cfg->reward[6], cfg->reward[7]};
     d.max_progress = hypotf_((float)WIDTH, (float)HEIGHT);
     d.seed = cfg->seed; d.env_base = cfg->env_id_base;
@@ -793,8 +796,70 @@ int isx_set_env_state(isx_handle* h, int32_t env, const isx_car_state* egos, con
     }
     CK(cudaMemcpy(d.step_count + env, &step_count, sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.tick + env, &tick, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // An injected state is a live episode: forget the end-of-episode flags of whatever ran before, or auto_reset would
+    // throw the injected state away at the start of the next step.
+    CK(cudaMemset(d.terminated + env, 0, 1));
+    CK(cudaMemset(d.truncated + env, 0, 1));
     return ISX_OK;
 }
+
+// Lidar.h:11-14 / IntersectionEnv.cpp:112-128,411-415: the beam count is a property of the Lidar objects, which the
+// reference swaps at run time (add_car_with_route builds 96-beam lidars, set_state leaves default 72-beam ones behind).
+// Here it is one setting of the handle: new relative angles, every stored hit cleared (a fresh Lidar reads 250 px on
+// every beam), obs columns beyond the new beam count zeroed, observation refreshed.  Synchronous.
+int isx_set_lidar_rays(isx_handle* h, int32_t rays) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (rays < 1 || rays > ISX_MAX_RAYS) return fail(ISX_E_ARG, "lidar_rays must be in [1,%d]", ISX_MAX_RAYS);
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<float> rel((size_t)ISX_MAX_RAYS, 0.0f);
+    lidar_rel_angles(rays, rel.data());
+    CK(cudaMemcpy(const_cast<float*>(h->d.rel_angle), rel.data(), sizeof(float) * rel.size(), cudaMemcpyHostToDevice));
+    h->d.R = rays;
+    for (auto& g : h->groups) { g.d.R = rays; g.cfg.lidar_rays = rays; }
+    const size_t EN = (size_t)h->d.E * h->d.N;
+    CK(cudaMemset(h->d.lidar_hit, 0, EN * ISX_MAX_RAYS));
+    CK(cudaMemset(h->d.obs, 0, sizeof(float) * EN * ISX_OBS_DIM));
+    if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }   // the captured launches carry the old Dev
+    const int rc = isx_observe(h, nullptr);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    return ISX_OK;
+}
+// Run-time setters of what the reference lets a caller change on a live env object (reward_config.* are def_readwrite,
+// bindings.cpp:33-42,63; configure / configure_traffic may be called at any time, IntersectionEnv.cpp:50-60).  group < 0 = all.
+// The settings travel to the kernels by value with every launch, so they take effect at the next step.
+static int for_groups(isx_handle* h, int32_t group, void (*fn)(isx_handle::Group&, const void*), const void* arg) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    if (group >= (int)h->groups.size()) return fail(ISX_E_ARG, "group %d out of range", group);
+    for (int g = 0; g < (int)h->groups.size(); ++g) if (group < 0 || group == g) fn(h->groups[(size_t)g], arg);
+    if (group <= 0) { const Dev& q = h->groups[0].d; h->d.rc = q.rc; h->d.use_team = q.use_team; h->d.respawn = q.respawn; h->d.max_steps = q.max_steps; }
+    if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }   // re-capture with the new settings
+    return ISX_OK;
+}
+int isx_set_reward(isx_handle* h, int32_t group, const float* k8) {
+    if (!k8) return fail(ISX_E_ARG, "null argument");
+    return for_groups(h, group, [](isx_handle::Group& g, const void* a) {
+        const float* k = static_cast<const float*>(a);
+        g.d.rc = RewardCfg{k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7]};
+        for (int i = 0; i < 8; ++i) g.cfg.reward[i] = k[i];
+    }, k8);
+}
+int isx_configure_episode(isx_handle* h, int32_t group, int32_t use_team, int32_t respawn, int32_t max_steps) {
+    const int v[3] = {use_team, respawn, max_steps};
+    return for_groups(h, group, [](isx_handle::Group& g, const void* a) {
+        const int* q = static_cast<const int*>(a);
+        g.d.use_team = q[0] != 0; g.d.respawn = q[1] != 0; g.d.max_steps = q[2];
+        g.cfg.use_team_reward = q[0]; g.cfg.respawn_enabled = q[1]; g.cfg.max_steps = q[2];
+    }, v);
+}
+int isx_set_traffic_density(isx_handle* h, int32_t group, float density) {
+    return for_groups(h, group, [](isx_handle::Group& g, const void* a) {
+        g.cfg.traffic_density = *static_cast<const float*>(a);
+        g.last_dt = -1.0f;                                    // spawn probability is cached per dt
+    }, &density);
+}
+int isx_lidar_rays(isx_handle* h) { return h ? h->d.R : fail(ISX_E_ARG, "null handle"); }
 
 int isx_snapshot_create(isx_handle* h, isx_snapshot** out) {
     if (!h || !out) return fail(ISX_E_ARG, "null argument");
@@ -879,14 +944,46 @@ int isx_stats_reset(isx_handle* h) {
     CK(cudaMemset(h->d.stats, 0, sizeof(unsigned long long) * 16));
     return ISX_OK;
 }
-int isx_stats_device_ptr(isx_handle* h, void** ptr, int32_t* n) {
-    if (!h || !ptr) return fail(ISX_E_ARG, "null argument");
+int isx_stats_device_ptrs(isx_handle* h, void** counters_i64, int32_t* n_counters, void** reward_sum_f64, void* stream) {
+    if (!h || !counters_i64 || !reward_sum_f64) return fail(ISX_E_ARG, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    CK(launch_reduce_stats(h->d, 0));
-    CK(cudaDeviceSynchronize());
-    *ptr = h->d.stats;
-    if (n) *n = 16;
+    CK(launch_reduce_stats(h->d, st));
+    CK(cudaStreamSynchronize(st));
+    *counters_i64 = h->d.stats;                       // int64[ISX_STATS_COUNTERS]: integers only, safe to all-reduce(sum) as int64
+    *reward_sum_f64 = h->d.stats + ISX_STATS_COUNTERS; // float64[1]: reduce separately, as a double
+    if (n_counters) *n_counters = ISX_STATS_COUNTERS;
     return ISX_OK;
+}
+
+// Car::update (Car.cpp:9-40) / Car::check_collision (Car.cpp:105-141) for detached car records, evaluated ON THE GPU by the
+// device functions the step kernels use (one thread; this is a unit-level convenience of the binding, not a fast path).
+static int car_unit(int32_t device, int op, isx_car_state* a, const isx_car_state* b, float thr, float st, float dt, int32_t* out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ISX_E_CUDA, "no CUDA device: this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail(ISX_E_ARG, "device %d out of range", device);
+    CK(cudaSetDevice(device));
+    float* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, sizeof(float) * 16));
+    float host[16] = {a->x, a->y, a->v, a->heading, a->acc, a->steer, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (b) { host[8] = b->x; host[9] = b->y; host[10] = b->heading; }
+    cudaError_t e = cudaMemcpy(buf, host, sizeof host, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_car_unit(op, buf, buf + 8, thr, st, dt, reinterpret_cast<int*>(buf + 12), 0);
+    if (e == cudaSuccess) e = cudaMemcpy(host, buf, sizeof host, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(ISX_E_CUDA, "car unit kernel failed: %s", cudaGetErrorString(e));
+    if (op == 0) { a->x = host[0]; a->y = host[1]; a->v = host[2]; a->heading = host[3]; a->acc = host[4]; a->steer = host[5]; }
+    else if (out) { int f; std::memcpy(&f, &host[12], 4); *out = f; }
+    return ISX_OK;
+}
+int isx_car_update(int32_t device, isx_car_state* car, float throttle, float steer_input, float dt) {
+    if (!car) return fail(ISX_E_ARG, "null argument");
+    return car_unit(device, 0, car, nullptr, throttle, steer_input, dt, nullptr);
+}
+int isx_car_check_collision(int32_t device, const isx_car_state* a, const isx_car_state* b, int32_t* collide) {
+    if (!a || !b || !collide) return fail(ISX_E_ARG, "null argument");
+    isx_car_state tmp = *a;
+    return car_unit(device, 1, &tmp, b, 0.0f, 0.0f, 0.0f, collide);
 }
 
 int isx_math_probe(int32_t device, int32_t n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr) {

@@ -57,7 +57,7 @@ constexpr int LOCKSTEP = ISX_LOCKSTEP;     // accelerated march steps every lane
 constexpr int ROAD_BITS_BYTES = ((ROAD_ROWS * ROAD_WORDS * 4 + 15) / 16) * 16;
 constexpr int ROAD_SKIP_BYTES = ((SKIP_DIM * SKIP_DIM + 15) / 16) * 16;
 
-#define ISX_STAMP(slot) do { if (d.trace && lane == 0) d.trace[(size_t)env * 16 + (slot)] = clock64(); } while (0)
+#define ISX_STAMP(slot) do { if (d.trace && env_ok && lane == 0) d.trace[(size_t)env * 16 + (slot)] = clock64(); } while (0)
 
 struct NpcSmem {
     float x[ISX_MAX_NPC], y[ISX_MAX_NPC], v[ISX_MAX_NPC], h[ISX_MAX_NPC], steer[ISX_MAX_NPC];
@@ -147,6 +147,8 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     uint32_t next_uid = d.next_uid[env];
     const bool reset_now = d.auto_reset && (d.terminated[env] | d.truncated[env]);   // env.py:147-152 after a done step
     if (reset_now) { c = 0; next_uid = 1; }
+    // auto_reset == 2 (next-step reset, see k_ego): the call that resets an env does not simulate it — no spawn draw, no tick
+    const bool frozen = reset_now && d.auto_reset == 2;
     const uint32_t tick = d.tick[env] + 1;
     ISX_STAMP(0);
 
@@ -164,7 +166,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     TrafficStream ts;
     ts.init(d.seed, genv, tick);
     {
-        const bool want = env_ok && ts.uniform01() < spawn_prob && d.T > 0;
+        const bool want = env_ok && !frozen && ts.uniform01() < spawn_prob && d.T > 0;
         int r = 0;
         bool blk = false;
         RouteMeta m{};
@@ -194,7 +196,7 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         }
         __syncwarp();
     }
-    evt.rng_draws = (int)ts.j;
+    evt.rng_draws = frozen ? 0 : (int)ts.j;
     ISX_STAMP(1);
 
     // -- NPC controller (:337-344).  The reference updates NPCs one after the other, NPC i seeing the already-updated
@@ -377,14 +379,20 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
         }
         step_count = 0; resets = 1;
     }
-    step_count += 1;                               // IntersectionEnv.cpp:137
-    const uint32_t tick = d.tick[env] + 1;
+    // auto_reset == 1: the reset happens at the start of the step and this call's action already drives the new episode
+    //   (the caller chose it looking at the terminal observation).
+    // auto_reset == 2: next-step reset as in Gymnasium's vector envs — the call after a terminated|truncated step only resets:
+    //   the action is ignored, nothing is simulated (step 0, tick unchanged, no traffic), reward 0, done 0, and the
+    //   observation returned is the one reset() returns (env.py:147-165: lidar part 1.0).
+    const bool frozen = resets != 0 && d.auto_reset == 2;
+    step_count += frozen ? 0 : 1;                  // IntersectionEnv.cpp:137
+    const uint32_t tick = d.tick[env] + (frozen ? 0u : 1u);
     const int c = d.traffic ? d.ncount[env] : 0;   // NPCs after this step's traffic update
 
     float rew = 0.0f;
     int status = ISX_ALIVE;
     bool done = false;
-    if (is_ego) {
+    if (is_ego && !frozen) {
         if (alive) {                               // :151-163
             float thr, st;
             if (actions) { thr = actions[2 * ai]; st = actions[2 * ai + 1]; }
@@ -401,10 +409,10 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
     unsigned cmask = 0;                            // bit j: ego a collides with ego j > a (sub-warp numbering)
     for (int dlt = 1; dlt < N; ++dlt) {
         const float ox = __shfl_down_sync(FULL, p.x, dlt, NP), oy = __shfl_down_sync(FULL, p.y, dlt, NP), oh = __shfl_down_sync(FULL, p.h, dlt, NP);
-        if (is_ego && a + dlt < N && cars_collide(p.x, p.y, p.h, ox, oy, oh)) cmask |= 1u << (a + dlt);
+        if (is_ego && !frozen && a + dlt < N && cars_collide(p.x, p.y, p.h, ox, oy, oh)) cmask |= 1u << (a + dlt);
     }
     bool npc_hit = false;
-    if (is_ego) {
+    if (is_ego && !frozen) {
         for (int k = 0; k < c && !npc_hit; ++k) {
             const int ni = env * d.M + k;
             npc_hit = cars_collide(p.x, p.y, p.h, d.nx[ni], d.ny[ni], d.nh[ni]);
@@ -459,6 +467,11 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
         d.esteer[ai] = steer; d.eacc[ai] = acc; d.epd[ai] = pd; d.epa0[ai] = pa0; d.epa1[ai] = pa1;
         d.epidx[ai] = pidx; d.ealive[ai] = alive ? 1 : 0;
         d.reward[ai] = rew; d.done[ai] = done ? 1 : 0; d.status[ai] = (uint8_t)status;
+        if (frozen) {                              // a fresh Lidar reads max range on every beam (Lidar.cpp:4-14)
+            uint4* hz = reinterpret_cast<uint4*>(d.lidar_hit + (size_t)ai * ISX_MAX_RAYS);
+#pragma unroll
+            for (int i = 0; i < ISX_MAX_RAYS / 16; ++i) hz[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         // lidar pixel rectangle of the (possibly respawned) ego for k_features / k_lidar_obs
         reinterpret_cast<PixRect*>(d.car_rect)[(size_t)env * (N + d.M) + a] = car_pixel_rect(p.x, p.y, p.h);
     }
@@ -474,13 +487,13 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
         for (int o = NP / 2; o > 0; o >>= 1) rs += __shfl_xor_sync(FULL, rs, o, NP);
         unsigned hist[6];
 #pragma unroll
-        for (int s6 = 0; s6 < 6; ++s6) hist[s6] = __popc((__ballot_sync(FULL, is_ego && status == s6) >> shift) & LOW);
+        for (int s6 = 0; s6 < 6; ++s6) hist[s6] = __popc((__ballot_sync(FULL, is_ego && !frozen && status == s6) >> shift) & LOW);
         if (env_ok && a == 0) {
             uint32_t* st = d.env_stats + (size_t)env * STAT_SLOTS;
 #pragma unroll
             for (int s6 = 0; s6 < 6; ++s6) if (hist[s6]) st[ST_HIST0 + s6] += hist[s6];
             if (resets) st[ST_RESETS] += resets;
-            st[ST_STEPS] += (uint32_t)N;
+            if (!frozen) st[ST_STEPS] += (uint32_t)N;
             double* ps = reinterpret_cast<double*>(st + ST_RSUM);
             *ps += rs;
         }
@@ -493,7 +506,7 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
 // (Lidar.cpp:65-78 as integer bounds) and, per ego, the packed list of cars a beam can possibly touch together with
 // the angular beam window of each (beam_window).  Cheap (<2% of the step): thread-per-ego, no shared memory.
 enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
-struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE, or -1 for a dead ego
+struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE; -1: dead ego (zero row); -2: beams come from the stored hits
 
 // Rare path of k_features: the reference's neighbour list of one ego (other alive egos in index order, then the NPCs in
 // list order, :466-488), ordered by the restated libstdc++ std::sort; returns the car index (ego j, or N + NPC j; 0xff = none) of ranks 0..4,
@@ -542,9 +555,12 @@ k_features(const Dev d, int mode) {
     const int nc = N + nn;
     const Pose me{d.ex[ga], d.ey[ga], d.ev[ga], d.eh[ga]};
     const bool alive = d.ealive[ga] != 0;
+    // next-step auto-reset (k_ego): an env that was only reset by this call has step 0 — its beams are not marched, the
+    // lidar part comes from the (cleared) stored hits, exactly like the observation reset() returns
+    const bool fresh = d.auto_reset == 2 && mode == LIDAR_MARCH && d.step_count[env] == 0;
     if (ok && q == 0) {
         AgentRec rec;
-        rec.x = me.x; rec.y = me.y; rec.h = me.h; rec.rect_base = alive ? env * CE : -1;
+        rec.x = me.x; rec.y = me.y; rec.h = me.h; rec.rect_base = alive ? (fresh ? -2 : env * CE) : -1;
         reinterpret_cast<AgentRec*>(d.agent_rec)[ga] = rec;
     }
     float bd[5]; int bk[5];
@@ -558,7 +574,7 @@ k_features(const Dev d, int mode) {
     const int nc_warp = __reduce_max_sync(FULL, nc);   // the ballot below needs every lane of the warp in the loop
     for (int k0 = 0; k0 < nc_warp; k0 += 4) {
         const int k = k0 + q;
-        const bool have = k < nc && alive;
+        const bool have = ok && k < nc && alive;   // padding quads (!ok) alias the last agent: they must not touch its lists
         float ox = 0, oy = 0, oh = 0;
         bool k_alive = true;
         if (have) {
@@ -568,7 +584,7 @@ k_features(const Dev d, int mode) {
         // ---- beam candidates.  Lidar.cpp:57-63: the ego itself, and anything within 1e-3 of its pose, is transparent;
         //      beams reach at most 248 px (+1 px truncation) from the origin pixel
         bool is_cand = false;
-        if (have && mode == LIDAR_MARCH) {
+        if (have && mode == LIDAR_MARCH && !fresh) {
             const bool same = fabsf(ox - me.x) < 1e-3f && fabsf(oy - me.y) < 1e-3f && fabsf(oh - me.h) < 1e-3f;
             if (!same) {
                 const PixRect r = rects[k];        // written by k_ego / k_traffic earlier in this step
@@ -749,14 +765,14 @@ k_lidar_obs(const Dev d, int mode) {
             const int ga = valid ? id / R : 0;
             const int i = valid ? id - ga * R : 0;
             const AgentRec rec = recs[ga];
+            const bool stored = valid && (mode == LIDAR_FROM_HITS ? rec.rect_base != -1 : rec.rect_base == -2);
             const bool alive = valid && rec.rect_base >= 0;
             float out = 0.0f;                                   // dead ego: all-zero row (:426-429)
-            if (mode == LIDAR_FROM_HITS) {
-                if (alive) {
-                    const int k = d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i];
-                    out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
-                }
-            } else {
+            if (stored) {
+                const int k = d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i];
+                out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
+            }
+            if (mode != LIDAR_FROM_HITS) {
                 Ray ray = make_ray(0.0f, 0.0f, 1.0f, 0.0f);
                 if (alive) {
                     float sn, cs;
@@ -969,6 +985,20 @@ __global__ void k_snapshot_restore(const SnapArray* __restrict__ tab, int n_arra
 // contraction canary: (a*b + c) with operands chosen so that a fused multiply-add gives a different float
 __global__ void k_canary(float a, float b, float c, float* out) { out[0] = a * b + c; double x = a, y = b, z = c; out[1] = (float)(x * y + z); }
 
+// Car::update / Car::check_collision on detached car records (the unit-level methods bindings.cpp:30-31 exposes on `Car`):
+// one thread, the same device functions the step kernels call.  io6 = {x, y, v, heading, acc, steering_angle}.
+__global__ void k_car_unit(int op, float* io6, const float* other3, float thr, float st, float dt, int* flag) {
+    if (op == 0) {
+        Pose p{io6[0], io6[1], io6[2], io6[3]};
+        float acc = io6[4], steer = io6[5];
+        car_update(p, steer, acc, thr, st, dt);
+        io6[0] = p.x; io6[1] = p.y; io6[2] = p.v; io6[3] = p.h; io6[4] = acc; io6[5] = steer;
+    } else {
+        // no far-apart shortcut semantics change: cars_collide is exact (see cars_far_apart)
+        *flag = cars_collide(io6[0], io6[1], io6[3], other3[0], other3[1], other3[2]) ? 1 : 0;
+    }
+}
+
 __global__ void k_math_probe(int n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1066,6 +1096,10 @@ cudaError_t launch_render(const Dev& d, int env, uint8_t* rgb, cudaStream_t st) 
 }
 cudaError_t launch_canary(float a, float b, float c, float* out, cudaStream_t st) {
     k_canary<<<1, 1, 0, st>>>(a, b, c, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_car_unit(int op, float* io6, const float* other3, float thr, float st, float dt, int* flag, cudaStream_t stm) {
+    k_car_unit<<<1, 1, 0, stm>>>(op, io6, other3, thr, st, dt, flag);
     return cudaGetLastError();
 }
 cudaError_t launch_math_probe(int n, const float* a, const float* b, float* sn, float* cs, float* tn, float* at, float* hy, float* wr, cudaStream_t st) {

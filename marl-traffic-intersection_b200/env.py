@@ -10,7 +10,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import cpp_backend
-from .utils import DEFAULT_REWARD_CONFIG, all_default_routes
+from .utils import DEFAULT_REWARD_CONFIG, all_default_routes, build_lane_layout
 
 # reward_config key -> RewardConfig attribute (env.py:57-77)
 _REWARD_ATTR = {
@@ -37,6 +37,9 @@ class IntersectionEnv:
         table = all_default_routes(self.num_lanes)                    # dict order of the default mapping (env.py:118-123)
         routes = get("ego_routes", None)
         self.ego_routes: Sequence[Tuple[str, str]] = routes if routes is not None else [table[i % len(table)] for i in range(self.num_agents)]
+
+        self.lane_layout = build_lane_layout(self.num_lanes)           # env.py:108-109 (Python-side only)
+        self.points = self.lane_layout["points"]
 
         core = cpp_backend.IntersectionEnv(self.num_lanes)
         core.seed, core.lidar_rays = int(get("seed", 0)), int(get("lidar_rays", 96))
@@ -105,7 +108,13 @@ class IntersectionEnv:
         return self._obs(out.obs), (scalar if self.traffic_flow else rew), done_flags[0], done_flags[1], info
 
     def render(self, show_lane_ids: Optional[bool] = None, show_lidar: Optional[bool] = None):
-        return self.env.render()   # headless: an rgb array instead of the reference's Windows/GLFW window
+        """env.py:210-217: nothing unless render_mode == "human".  The reference then draws into its Windows/GLFW window;
+        here the same call returns the headless picture (uint8 [750, 750, 3]) of isx_render."""
+        if self.render_mode != "human":
+            return None
+        lane_ids = self.show_lane_ids if show_lane_ids is None else show_lane_ids
+        lidar = self.show_lidar if show_lidar is None else show_lidar
+        return self.env.render(bool(lane_ids), bool(lidar))
 
     def close(self):
         if getattr(self.env, "_benv", None) is not None:

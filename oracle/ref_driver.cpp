@@ -140,6 +140,8 @@ void isxref_set_ego_routes(void *h, int n, const char *const *starts, const char
     for (int i = 0; i < n; ++i) r->ego_routes.emplace_back(starts[i], ends[i]);
 }
 void isxref_set_lidar_rays(void *h, int rays) { static_cast<RefEnv *>(h)->lidar_rays = rays; }
+/* Mid-episode switch to the 72-beam variant: what IntersectionEnv::set_state does to the lidars (IntersectionEnv.cpp:411-415). */
+void isxref_swap_lidars(void *h) { static_cast<RefEnv *>(h)->apply_lidar_variant(); }
 
 /* env.reset() followed by add_car_with_route per ego, as env.py:147-152 does. */
 int isxref_reset(void *h) {

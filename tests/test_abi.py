@@ -65,7 +65,7 @@ def test_no_cpu_fallback():
     # the C entry point itself refuses without a device
     lib = _lib.load_library()
     cfg = _lib.Config()
-    cfg.abi_version, cfg.num_envs, cfg.num_agents, cfg.num_lanes, cfg.lidar_rays = 1, 1, 1, 3, 96
+    cfg.abi_version, cfg.num_envs, cfg.num_agents, cfg.num_lanes, cfg.lidar_rays = _lib.ISX_ABI_VERSION, 1, 1, 3, 96
     s, e = (C.c_char_p * 1)(b"IN_6"), (C.c_char_p * 1)(b"OUT_2")
     cfg.ego_start, cfg.ego_end = s, e
     h = C.c_void_p()
@@ -83,7 +83,7 @@ def test_config_validation_happens_before_any_device_work():
 
     def cfg(**kw):
         c = _lib.Config()
-        c.abi_version, c.num_envs, c.num_agents, c.num_lanes, c.lidar_rays = 1, 4, 3, 3, 96
+        c.abi_version, c.num_envs, c.num_agents, c.num_lanes, c.lidar_rays = _lib.ISX_ABI_VERSION, 4, 3, 3, 96
         c.ego_start, c.ego_end = s, e
         for k, v in kw.items():
             setattr(c, k, v)

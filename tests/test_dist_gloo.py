@@ -23,7 +23,7 @@ def shard(rank, world, total):
 
 
 def counters_for(env_ids):
-    v = np.zeros(16, np.int64)                      # layout of isx_stats_device_ptr: hist[0:6] ... steps[11]
+    v = np.zeros(15, np.int64)                      # layout of isx_stats_device_ptrs: int64[15], hist[0:6] ... agent_steps[11]
     rsum = 0.0
     for g in env_ids:
         e = po.OracleEnv(3, ROUTES, traffic=True, density=2.0, max_steps=120, seed=SEED, env_id=g)
@@ -40,10 +40,18 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     v, rsum = counters_for(shard(rank, world, GLOBAL_ENVS))
+    # the product's own reduction (BatchedIntersectionEnv.reduce_stats -> reduce_stat_tensors): int64 counters and the
+    # float64 reward sum are reduced as two tensors — summing a double's bit pattern as an integer would be garbage
+    from marl_traffic_intersection_b200.batched import reduce_stat_tensors
     t = torch.from_numpy(v)
     r = torch.tensor([rsum], dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    tot = reduce_stat_tensors(t, r)
+    assert tot["agent_steps"] == int(t[11]) and tot["reward_sum"] == float(r[0])
+    try:
+        reduce_stat_tensors(torch.zeros(16, dtype=torch.int64), torch.zeros(1, dtype=torch.int64))
+        raise SystemExit("a reward sum carried as int64 must be refused")
+    except TypeError:
+        pass
     tmax = torch.tensor([float(rank + 1)], dtype=torch.float64)   # bench.py takes the MAX time over ranks
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     if rank == 0:

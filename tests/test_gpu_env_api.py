@@ -8,11 +8,16 @@ import pyoracle as po
 pytestmark = pytest.mark.gpu
 
 
+def Checker(*a, **k):
+    """The reference's own C++ when oracle/_ref travelled with the repo, else the pinned C port."""
+    return (po.RefEnv if po.have_ref() else po.OracleEnv)(*a, **k)
+
+
 def test_multi_agent_surface_and_values():
     from marl_traffic_intersection_b200 import IntersectionEnv
     routes = [("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")]
     env = IntersectionEnv({"num_agents": 3, "use_team_reward": True, "ego_routes": routes})
-    ref = po.OracleEnv(3, routes, use_team=True)
+    ref = Checker(3, routes, use_team=True)
     obs, info = env.reset()
     assert obs.shape == (3, 127) and obs.dtype == np.float32 and info == {}
     assert (obs.view(np.uint32) == ref.obs().view(np.uint32)).all()
@@ -41,7 +46,7 @@ def test_traffic_mode_forces_single_agent_and_scalar_returns():
     assert env.num_agents == 1                          # env.py:87-90
     obs, _ = env.reset()
     assert obs.shape == (127,)
-    ref = po.OracleEnv(3, [("IN_1", "OUT_4")], traffic=True, density=2.0, seed=3)
+    ref = Checker(3, [("IN_1", "OUT_4")], traffic=True, density=2.0, seed=3)
     for _ in range(200):
         obs, rew, term, trunc, info = env.step([0.3, 0.0])
         r = ref.step([[0.3, 0.0]])
@@ -105,10 +110,11 @@ def test_headless_render_shows_road_cars_and_hits():
     assert seen_hit > 0 and ((img == [220, 30, 30]).all(-1)).sum() >= 5
     # the single-env facade returns the same kind of picture
     from marl_traffic_intersection_b200 import IntersectionEnv
-    env = IntersectionEnv({"num_agents": 2, "ego_routes": R3[:2]})
-    assert env.render() is None or env.render().shape == (750, 750, 3)
-    env.reset()
+    env = IntersectionEnv({"num_agents": 2, "ego_routes": R3[:2], "render_mode": "human"})
     pic = env.render()
     assert pic.shape == (750, 750, 3) and (pic[int(env.env.cars[0].state.y), int(env.env.cars[0].state.x)] == [231, 76, 60]).all()
+    quiet = IntersectionEnv({"num_agents": 2, "ego_routes": R3[:2]})
+    assert quiet.render() is None                      # env.py:210-212: nothing unless render_mode == "human"
+    quiet.close()
     env.close()
     b.close()
