@@ -136,7 +136,7 @@ typedef struct isx_stats {
 /* Environment switches read at isx_create (tuning / bisecting aids, all optional): ISX_NO_PDL=1 (fully serialised kernel
  * launches instead of programmatic dependent launch), ISX_NO_GRAPH=1 (host-buffer step on the stream path instead of the
  * captured CUDA graph), ISX_PIPE_PLAN="w0,w1,..." (env ranges of the host-step pipeline), ISX_LIDAR_CTAS_PER_SM=n (cap of
- * the persistent beam-kernel grid), ISX_TRACE=1 (per-env phase stamps, isx_trace_read). */
+ * the persistent beam-kernel grid), ISX_HOST_THREADS=n (host threads completing obs rows), ISX_TRACE=1 (per-env phase stamps, isx_trace_read). */
 const char *isx_last_error(void);
 int isx_abi_version(void);
 
@@ -176,6 +176,16 @@ int isx_step_host(isx_handle *h, const float *actions, float dt, float *obs, flo
 int isx_step_pinned(isx_handle *h, float dt, void *stream);
 int isx_host_views(isx_handle *h, float **actions, float **obs, float **reward, uint8_t **done, uint8_t **status,
                    uint8_t **terminated, uint8_t **truncated);
+/* What one host-buffer step moves and who completes the rows: bytes host->device (actions), bytes device->host (per agent a
+ * compact obs record of 32 floats + lidar_rays hit-index bytes instead of the 127-float row — the lidar columns are exactly
+ * float(4k)/250 of the hit index k and the columns behind the last beam are 0, so the rows are rebuilt bit-identically in
+ * host memory by `host_threads` worker threads while later env ranges are still in flight; 0 threads = inline — plus the
+ * reward/done/status/flags block), and the number of pipeline ranges.  ISX_HOST_THREADS=n overrides the thread count
+ * (default: the CPUs this process may run on, at most 32). */
+int isx_host_step_info(isx_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes, int32_t *host_threads, int32_t *ranges);
+/* The host half of that transport on its own (pure host code, no device needed): n compact records (32 floats: obs[0..30]
+ * + alive flag) and n x lidar_rays hit indices -> n obs rows of 127 floats, exactly as the device writes them. */
+int isx_expand_obs_rows(const float *records32, const uint8_t *hit_index, int32_t lidar_rays, float *obs_rows, int64_t n_agents);
 /* Two more pinned views filled by the same step: agents_alive [E] and step [E] (int32), StepResult.agents_alive / .step
  * of bindings.cpp:27-36. */
 int isx_host_views_aux(isx_handle *h, int32_t **agents_alive, int32_t **step);

@@ -73,7 +73,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "isx_last_error", "isx_abi_version", "isx_create", "isx_create_groups", "isx_num_groups", "isx_group_range", "isx_destroy", "isx_reset", "isx_step", "isx_step_host",
-    "isx_step_pinned", "isx_host_views", "isx_host_views_aux",
+    "isx_step_pinned", "isx_host_views", "isx_host_views_aux", "isx_host_step_info", "isx_expand_obs_rows",
     "isx_rollout", "isx_rollout_timed", "isx_rollout_timed4", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
     "isx_observe", "isx_render", "isx_snapshot_create", "isx_snapshot_save", "isx_snapshot_restore", "isx_snapshot_destroy",
     "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_pipe_timeline", "isx_stats_device_ptrs", "isx_route", "isx_math_probe",
@@ -111,6 +111,8 @@ def load_library(path: str | None = None):
     lib.isx_step_pinned.argtypes = [vp, f32, vp]
     lib.isx_host_views.argtypes = [vp] + [C.POINTER(vp)] * 7
     lib.isx_host_views_aux.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.isx_expand_obs_rows.argtypes = [vp, vp, i32, vp, C.c_int64]
+    lib.isx_host_step_info.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32), C.POINTER(i32)]
     lib.isx_rollout.argtypes = [vp, i32, f32, vp]
     lib.isx_rollout_timed.argtypes = [vp, i32, f32, vp, C.POINTER(f32), C.POINTER(f32)]
     lib.isx_rollout_timed4.argtypes = [vp, i32, f32, vp, C.POINTER(f32)]

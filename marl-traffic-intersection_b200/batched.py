@@ -242,6 +242,13 @@ class BatchedIntersectionEnv:
             out = tuple(np.array(x) for x in out)
         return out
 
+    def host_step_bytes(self) -> Dict[str, Any]:
+        """What one step_host() moves over PCIe and who completes the obs rows on the host (isx_host_step_info)."""
+        a, b, t, r = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        _lib.check(self._lib, self._lib.isx_host_step_info(self._h, C.byref(a), C.byref(b), C.byref(t), C.byref(r)))
+        return {"h2d": a.value, "d2h": b.value, "host_expand_threads": t.value, "pipeline_ranges": r.value,
+                "obs_transport": "compact: 32 f32 + lidar_rays u8 per agent over PCIe, 127-float rows rebuilt bit-identically by host threads"}
+
     def rollout(self, steps: int, dt: float = 1.0 / 60.0):
         """`steps` steps with on-device Philox actions (random-action rollout of BASELINE.json)."""
         _lib.check(self._lib, self._lib.isx_rollout(self._h, int(steps), C.c_float(dt), self._stream()))

@@ -41,9 +41,9 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> None:
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [
         os.path.join(HERE, "..", "include", "isx.h")]
     lib = os.path.join(CSRC, "libisx_b200.so")
-    srcs = [os.path.join(CSRC, "isx_kernels.cu"), os.path.join(CSRC, "isx_api.cu")]
+    srcs = [os.path.join(CSRC, "isx_kernels.cu"), os.path.join(CSRC, "isx_api.cu"), os.path.join(CSRC, "isx_host_expand.cpp")]
     if force or _newer(lib, srcs + hdrs):
-        _run([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["isx_kernels.cu", "isx_api.cu", "-o", lib])
+        _run([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["isx_kernels.cu", "isx_api.cu", "isx_host_expand.cpp", "-o", lib])
     for name in ("isx_math_host", "isx_host_units"):
         out = os.path.join(CSRC, f"lib{name}.so")
         src = os.path.join(CSRC, name + ".cpp")

@@ -7,10 +7,17 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include <sched.h>
+
 #include "isx_device.cuh"
+#include "isx_host_expand.h"
 #include "isx_tables.h"
 
 namespace isx {
@@ -52,6 +59,74 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(ISX_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// ---- host threads that complete the obs rows of a host-buffer step (isx_host_expand.cpp) while later env ranges are still
+// being simulated / copied.  Worker w owns a fixed slice of every pipeline range; a range becomes available when the host
+// callback queued behind its device->host copies fires.  No queues, no locks on the data path.
+struct ExpandPool {
+    struct Range { size_t a0, a1; };                 // agent range of one pipeline piece
+    std::vector<std::thread> threads;
+    std::vector<Range> ranges;
+    std::mutex mu;
+    std::condition_variable cv_start, cv_done;
+    std::atomic<uint64_t> seq{0};                    // step sequence number, bumped by the caller to start a step
+    std::atomic<uint64_t> ready[64];                 // ready[c] == seq once range c's compact records are in host memory
+    int done = 0;
+    bool quit = false;
+    // the job of the current step
+    const float* rec = nullptr; const uint8_t* hits = nullptr; float* dst = nullptr; int R = 0;
+
+    void worker(int w, int T) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_start.wait(lk, [&] { return quit || seq.load() != seen; });
+                if (quit) return;
+                seen = seq.load();
+            }
+            for (size_t c = 0; c < ranges.size(); ++c) {
+                int spins = 0;
+                while (ready[c].load(std::memory_order_acquire) < seen) {
+                    if (++spins < 4096) __builtin_ia32_pause(); else { std::this_thread::yield(); spins = 0; }
+                }
+                // slices are cut at multiples of 8 rows so that each starts 32-byte aligned (non-temporal store path)
+                const size_t n = ranges[c].a1 - ranges[c].a0, blocks = (n + 7) / 8;
+                const size_t b0 = blocks * (size_t)w / (size_t)T, b1 = blocks * (size_t)(w + 1) / (size_t)T;
+                const size_t r0 = ranges[c].a0 + b0 * 8, r1 = ranges[c].a0 + (b1 * 8 < n ? b1 * 8 : n);
+                if (r1 > r0) expand_obs_rows(rec + r0 * 32, hits + r0 * (size_t)R, R, dst + r0 * ISX_OBS_DIM, r1 - r0);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (++done == T) cv_done.notify_one();
+            }
+        }
+    }
+    void start(int T) {
+        for (auto& r : ready) r.store(0);
+        for (int w = 0; w < T; ++w) threads.emplace_back([this, w, T] { worker(w, T); });
+    }
+    void begin_step(const float* rec_, const uint8_t* hits_, float* dst_, int R_) {
+        std::lock_guard<std::mutex> lk(mu);
+        rec = rec_; hits = hits_; dst = dst_; R = R_; done = 0; seq.fetch_add(1);
+        cv_start.notify_all();
+    }
+    void release_all() { for (auto& r : ready) r.store(seq.load(), std::memory_order_release); }   // error path: let the workers finish
+    void wait_step() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return done == (int)threads.size(); });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; cv_start.notify_all(); }
+        for (auto& t : threads) t.join();
+        threads.clear();
+    }
+};
+struct ExpandSignal { ExpandPool* pool; int range; };
+static void CUDART_CB expand_range_ready(void* p) {
+    ExpandSignal* s = static_cast<ExpandSignal*>(p);
+    s->pool->ready[s->range].store(s->pool->seq.load(), std::memory_order_release);   // seq is stable while a step is in flight
+}
+
 struct isx_handle {
     // One homogeneous slice of the batch (isx_create_groups): its own settings / tables over an env range of the buffers.
     struct Group {
@@ -71,6 +146,11 @@ struct isx_handle {
     // pinned staging for isx_step_host
     float* h_actions = nullptr; float* d_actions = nullptr;
     float* h_obs = nullptr; float* h_reward = nullptr;
+    float* h_rec = nullptr; uint8_t* h_hitc = nullptr;   // pinned landing zone of the compact obs records (isx_host_expand.cpp)
+    ExpandPool* pool = nullptr;                          // null: rows are completed inline after the step (small batches)
+    std::vector<ExpandSignal> signals;
+    float* expand_dst = nullptr;                         // where this step's rows go (h_obs or the caller's buffer)
+    int host_threads = 0;
     uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;   // views into h_small
     uint8_t *d_small = nullptr, *h_small = nullptr;      // reward | done | status | terminated | truncated, one block each side
     size_t small_off[7] = {0, 0, 0, 0, 0, 0, 0}, small_bytes = 0;
@@ -95,6 +175,7 @@ static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
     s.ncount += oE; s.next_uid += oE; s.step_count += oE; s.tick += oE;
     s.agent_rec = static_cast<char*>(d.agent_rec) + oEN * 16; s.car_rect = static_cast<char*>(d.car_rect) + oEC * 16;
     s.cand += oEN * (size_t)(d.N + d.M); s.cand_n += oEN; s.ray_counter = d.ray_counter + shard_idx;
+    s.obs_c += oEN * 32; s.hit_c += oEN * (size_t)d.R;
     s.obs += oEN * ISX_OBS_DIM; s.reward += oEN; s.done += oEN; s.status += oEN;
     s.terminated += oE; s.truncated += oE; s.agents_alive += oE; s.lidar_hit += oEN * ISX_MAX_RAYS;
     s.events += oE; s.env_stats += oE * STAT_SLOTS;
@@ -299,6 +380,7 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
     ALLOC(d.npidx, EM); ALLOC(d.nroute, EM); ALLOC(d.nuid, EM);
     ALLOC(d.ncount, E); ALLOC(d.next_uid, E); ALLOC(d.tick, E);
     ALLOC(d.obs, EN * ISX_OBS_DIM);
+    ALLOC(d.obs_c, EN * 32); ALLOC(d.hit_c, EN * ISX_MAX_RAYS);     // hit_c is used densely at stride R (<= 96)
     {
         // reward | done | status | terminated | truncated | agents_alive | step live in ONE block (sub-arrays 256 B
         // aligned), mirrored by one pinned host block, so the host-buffer step brings all of them back with a single copy
@@ -376,10 +458,13 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
     // pinned staging
     if (cudaMallocHost((void**)&h->h_actions, sizeof(float) * EN * 2) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_obs, sizeof(float) * EN * ISX_OBS_DIM) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_small, h->small_bytes) != cudaSuccess) {
+        cudaMallocHost((void**)&h->h_small, h->small_bytes) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_rec, sizeof(float) * EN * 32) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_hitc, EN * ISX_MAX_RAYS) != cudaSuccess) {
         isx_destroy(h);
         return fail(ISX_E_CUDA, "pinned host allocation failed");
     }
+    std::memset(h->h_obs, 0, sizeof(float) * EN * ISX_OBS_DIM);
     h->h_reward = reinterpret_cast<float*>(h->h_small + h->small_off[0]);
     h->h_done = h->h_small + h->small_off[1]; h->h_status = h->h_small + h->small_off[2];
     h->h_term = h->h_small + h->small_off[3]; h->h_trunc = h->h_small + h->small_off[4];
@@ -415,6 +500,27 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
             for (int g = 0; g < n_groups; ++g) h->pipe.push_back(isx_handle::Piece{g, 0, h->groups[(size_t)g].d.E});
         }
         h->ev_shard.resize(h->pipe.size(), nullptr);
+        // Host threads completing the obs rows: as many as this process may run on (the caller binds ranks to disjoint CPU
+        // sets), ISX_HOST_THREADS overrides; small batches finish their rows inline, without callbacks or thread wake-ups.
+        int T = 0;
+        cpu_set_t cs;
+        if (sched_getaffinity(0, sizeof cs, &cs) == 0) T = CPU_COUNT(&cs);
+        if (T < 1) T = (int)std::thread::hardware_concurrency();
+        if (T > 32) T = 32;
+        if (const char* ht = getenv("ISX_HOST_THREADS")) { const int v = atoi(ht); if (v >= 0 && v <= 256) T = v; }
+        if (EN < 4096 || h->pipe.size() > 64) T = 0;
+        h->host_threads = T;
+        if (T > 0) {
+            h->pool = new ExpandPool();
+            h->signals.resize(h->pipe.size());
+            for (size_t c = 0; c < h->pipe.size(); ++c) {
+                const isx_handle::Piece& pc = h->pipe[c];
+                const size_t a0 = (size_t)(h->groups[(size_t)pc.group].first + pc.e0) * d.N;
+                h->pool->ranges.push_back(ExpandPool::Range{a0, a0 + (size_t)pc.cnt * d.N});
+                h->signals[c] = ExpandSignal{h->pool, (int)c};
+            }
+            h->pool->start(T);
+        }
     }
     {
         cudaError_t e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
@@ -436,6 +542,7 @@ int isx_destroy(isx_handle* h) {
     if (!h) return ISX_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->pool) { h->pool->stop(); delete h->pool; h->pool = nullptr; }
     for (void* p : h->allocs) cudaFree(p);
     if (h->pipe_exec) cudaGraphExecDestroy(h->pipe_exec);
     if (h->pipe_stream) cudaStreamDestroy(h->pipe_stream);
@@ -446,6 +553,8 @@ int isx_destroy(isx_handle* h) {
     if (h->h_actions) cudaFreeHost(h->h_actions);
     if (h->h_obs) cudaFreeHost(h->h_obs);
     if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->h_rec) cudaFreeHost(h->h_rec);
+    if (h->h_hitc) cudaFreeHost(h->h_hitc);
     delete h;
     return ISX_OK;
 }
@@ -582,7 +691,10 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::ve
         CK(cudaEventRecord(h->ev_shard[c], st));
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_shard[c], 0));
         if (tl) CK(cudaEventRecord((*tl)[3 + 4 * c], h->copy_stream));
-        CK(cudaMemcpyAsync(h->h_obs + aoff * ISX_OBS_DIM, d.obs + aoff * ISX_OBS_DIM, sizeof(float) * an * ISX_OBS_DIM, cudaMemcpyDeviceToHost, h->copy_stream));
+        // the compact obs record of the range (32 floats + R bytes per agent instead of 127 floats); host threads rebuild the rows
+        CK(cudaMemcpyAsync(h->h_rec + aoff * 32, d.obs_c + aoff * 32, sizeof(float) * an * 32, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(h->h_hitc + aoff * (size_t)d.R, d.hit_c + aoff * (size_t)d.R, an * (size_t)d.R, cudaMemcpyDeviceToHost, h->copy_stream));
+        if (h->pool) CK(cudaLaunchHostFunc(h->copy_stream, expand_range_ready, &h->signals[c]));
         if (tl) CK(cudaEventRecord((*tl)[4 + 4 * c], h->copy_stream));
     }
     // the stream order of copy_stream puts this after the last shard's kernels (its wait on ev_shard[last])
@@ -599,34 +711,50 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::ve
 // The whole step (1 + shards copies in, 4 kernels and 1 copy out per shard, the fork/join events) is captured ONCE per
 // dt into a CUDA graph and replayed with a single launch: issuing ~35 runtime calls per step from the host costs more
 // than the first shards take to run.  ISX_NO_GRAPH=1 at isx_create keeps the plain stream path.
+// One host-buffer step whose obs rows land in `dst` ([E*N][127] floats in host memory).  Synchronous.
+static int host_step_into(isx_handle* h, float dt, cudaStream_t st, float* dst, std::vector<cudaEvent_t>* tl = nullptr) {
+    CK(cudaSetDevice(h->device));
+    if (h->pool) h->pool->begin_step(h->h_rec, h->h_hitc, dst, h->d.R);
+    auto run = [&]() -> int {
+        if (!h->use_graph || tl) {
+            const int rc = enqueue_pinned_step(h, dt, st, tl);
+            if (rc) return rc;
+            CK(cudaEventSynchronize(h->ev_copy_done));
+            CK(cudaStreamSynchronize(h->copy_stream));           // host callbacks of the last range included
+            return ISX_OK;
+        }
+        if (!h->pipe_exec || std::memcmp(&h->pipe_dt, &dt, sizeof dt) != 0) {
+            if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(h->pipe_stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_pinned_step(h, dt, h->pipe_stream);
+            const cudaError_t ce = cudaStreamEndCapture(h->pipe_stream, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            CK(ce);
+            const cudaError_t ie = cudaGraphInstantiate(&h->pipe_exec, g, 0);
+            cudaGraphDestroy(g);
+            CK(ie);
+            h->pipe_dt = dt;
+        }
+        CK(cudaEventRecord(h->ev_pipe_in, st));                  // order the replay after whatever the caller queued on `st`
+        CK(cudaStreamWaitEvent(h->pipe_stream, h->ev_pipe_in, 0));
+        CK(cudaGraphLaunch(h->pipe_exec, h->pipe_stream));
+        CK(cudaStreamSynchronize(h->pipe_stream));
+        return ISX_OK;
+    };
+    const int rc = run();
+    if (h->pool) {
+        if (rc) h->pool->release_all();
+        h->pool->wait_step();                                    // every row of `dst` is complete (and fenced) after this
+    } else if (!rc) {
+        expand_obs_rows(h->h_rec, h->h_hitc, h->d.R, dst, (size_t)h->d.E * h->d.N);
+    }
+    return rc;
+}
+
 int isx_step_pinned(isx_handle* h, float dt, void* stream) {
     if (!h) return fail(ISX_E_ARG, "null handle");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CK(cudaSetDevice(h->device));
-    if (!h->use_graph) {
-        const int rc = enqueue_pinned_step(h, dt, st);
-        if (rc) return rc;
-        CK(cudaEventSynchronize(h->ev_copy_done));
-        return ISX_OK;
-    }
-    if (!h->pipe_exec || std::memcmp(&h->pipe_dt, &dt, sizeof dt) != 0) {
-        if (h->pipe_exec) { cudaGraphExecDestroy(h->pipe_exec); h->pipe_exec = nullptr; }
-        cudaGraph_t g = nullptr;
-        CK(cudaStreamBeginCapture(h->pipe_stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = enqueue_pinned_step(h, dt, h->pipe_stream);
-        const cudaError_t ce = cudaStreamEndCapture(h->pipe_stream, &g);
-        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-        CK(ce);
-        const cudaError_t ie = cudaGraphInstantiate(&h->pipe_exec, g, 0);
-        cudaGraphDestroy(g);
-        CK(ie);
-        h->pipe_dt = dt;
-    }
-    CK(cudaEventRecord(h->ev_pipe_in, st));                  // order the replay after whatever the caller queued on `st`
-    CK(cudaStreamWaitEvent(h->pipe_stream, h->ev_pipe_in, 0));
-    CK(cudaGraphLaunch(h->pipe_exec, h->pipe_stream));
-    CK(cudaStreamSynchronize(h->pipe_stream));
-    return ISX_OK;
+    return host_step_into(h, dt, static_cast<cudaStream_t>(stream), h->h_obs);
 }
 
 // Tuning aid: ONE host-buffer step on the plain stream path with timing events around every range's kernels and copy.
@@ -640,10 +768,8 @@ int isx_pipe_timeline(isx_handle* h, float dt, void* stream, float* ms, int32_t 
     if ((size_t)cap_ranges < n) return fail(ISX_E_ARG, "need room for %d ranges", (int)n);
     std::vector<cudaEvent_t> ev(1 + 4 * n);
     for (auto& e : ev) CK(cudaEventCreate(&e));
-    const int rc = enqueue_pinned_step(h, dt, st, &ev);
+    const int rc = host_step_into(h, dt, st, h->h_obs, &ev);
     if (rc) return rc;
-    CK(cudaEventSynchronize(h->ev_copy_done));
-    CK(cudaStreamSynchronize(h->copy_stream));
     for (size_t i = 0; i < 4 * n; ++i) CK(cudaEventElapsedTime(&ms[i], ev[0], ev[1 + i]));
     for (auto& e : ev) cudaEventDestroy(e);
     return (int)n;
@@ -662,6 +788,23 @@ int isx_host_views(isx_handle* h, float** actions, float** obs, float** reward, 
     return ISX_OK;
 }
 
+int isx_expand_obs_rows(const float* records32, const uint8_t* hit_index, int32_t lidar_rays, float* obs_rows, int64_t n_agents) {
+    if (!records32 || !hit_index || !obs_rows) return fail(ISX_E_ARG, "null argument");
+    if (lidar_rays < 1 || lidar_rays > ISX_MAX_RAYS || n_agents < 0) return fail(ISX_E_ARG, "bad sizes");
+    expand_obs_rows(records32, hit_index, lidar_rays, obs_rows, (size_t)n_agents);
+    return ISX_OK;
+}
+
+int isx_host_step_info(isx_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int32_t* host_threads, int32_t* ranges) {
+    if (!h) return fail(ISX_E_ARG, "null handle");
+    const int64_t EN = (int64_t)h->d.E * h->d.N;
+    if (h2d_bytes) *h2d_bytes = EN * 2 * (int64_t)sizeof(float);
+    if (d2h_bytes) *d2h_bytes = EN * (32 * (int64_t)sizeof(float) + h->d.R) + (int64_t)h->small_bytes;
+    if (host_threads) *host_threads = h->host_threads;
+    if (ranges) *ranges = (int32_t)h->pipe.size();
+    return ISX_OK;
+}
+
 int isx_host_views_aux(isx_handle* h, int32_t** agents_alive, int32_t** step) {
     if (!h) return fail(ISX_E_ARG, "null handle");
     if (agents_alive) *agents_alive = reinterpret_cast<int32_t*>(h->h_small + h->small_off[5]);
@@ -676,9 +819,9 @@ int isx_step_host(isx_handle* h, const float* actions, float dt, float* obs, flo
     const Dev& d = h->d;
     const size_t EN = (size_t)d.E * d.N, E = (size_t)d.E;
     std::memcpy(h->h_actions, actions, sizeof(float) * EN * 2);
-    const int rc = isx_step_pinned(h, dt, stream);
+    // the obs rows are completed straight into the caller's buffer (no staging copy of 127 floats per agent)
+    const int rc = host_step_into(h, dt, static_cast<cudaStream_t>(stream), obs ? obs : h->h_obs);
     if (rc) return rc;
-    if (obs) std::memcpy(obs, h->h_obs, sizeof(float) * EN * ISX_OBS_DIM);
     if (reward) std::memcpy(reward, h->h_reward, sizeof(float) * EN);
     if (done) std::memcpy(done, h->h_done, EN);
     if (status) std::memcpy(status, h->h_status, EN);

@@ -52,6 +52,8 @@ struct Dev {
     int* cand_n;                 // [E][N]
     unsigned* ray_counter;       // [1] dynamic work counter of k_lidar_obs
     // ---- outputs
+    float* obs_c;                // [E][N][32]  compact record for the host-buffer step: obs[0..30] + alive flag (isx_host_expand.cpp)
+    uint8_t* hit_c;              // [E][N][R]   lidar hit indices, dense stride R (what crosses PCIe instead of the float lidar columns)
     float* obs;                  // [E][N][127]
     float* reward;               // [E][N]
     uint8_t *done, *status;      // [E][N]

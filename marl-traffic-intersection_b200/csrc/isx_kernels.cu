@@ -620,6 +620,7 @@ k_features(const Dev d, int mode) {
         }
     }
     float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
+    float* crow = d.obs_c + (size_t)ga * 32;       // compact copy of the same 31 floats (+ alive flag) for the host-buffer step
     // ---- merge the four sorted partial lists: five rounds of a quad-wide lexicographic (distance, list index) minimum,
     //      plus a sixth minimum that is only looked at for the tie test below
     float fd[6]; int fk[5];
@@ -672,7 +673,7 @@ k_features(const Dev d, int mode) {
             obs_neighbor_features(me, ot, intent, f5);
         }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) orow[6 + 5 * r + i] = f5[i];
+        for (int i = 0; i < 5; ++i) { orow[6 + 5 * r + i] = f5[i]; crow[6 + 5 * r + i] = f5[i]; }
     }
     if (ok && q == 1) {                            // the six ego features (:431-458); zeros for a dead ego (:426-429)
         float f6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -681,7 +682,8 @@ k_features(const Dev d, int mode) {
             obs_ego_features(me, path[min(d.epidx[ga] + 10, PATH_LEN - 1)], f6);
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) orow[i] = f6[i];
+        for (int i = 0; i < 6; ++i) { orow[i] = f6[i]; crow[i] = f6[i]; }
+        crow[31] = alive ? 1.0f : 0.0f;
     }
 }
 
@@ -768,9 +770,11 @@ k_lidar_obs(const Dev d, int mode) {
             const bool stored = valid && (mode == LIDAR_FROM_HITS ? rec.rect_base != -1 : rec.rect_base == -2);
             const bool alive = valid && rec.rect_base >= 0;
             float out = 0.0f;                                   // dead ego: all-zero row (:426-429)
+            int kout = 0;                                       // hit index behind `out` (compact copy for the host-buffer step)
             if (stored) {
                 const int k = d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i];
                 out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
+                kout = k;
             }
             if (mode != LIDAR_FROM_HITS) {
                 Ray ray = make_ray(0.0f, 0.0f, 1.0f, 0.0f);
@@ -798,9 +802,13 @@ k_lidar_obs(const Dev d, int mode) {
                     }
                     d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i] = (uint8_t)best;
                     out = (best ? (float)(4 * best) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
+                    kout = best;
                 }
             }
-            if (valid) d.obs[(size_t)ga * ISX_OBS_DIM + 31 + i] = out;
+            if (valid) {
+                d.obs[(size_t)ga * ISX_OBS_DIM + 31 + i] = out;
+                d.hit_c[id] = (uint8_t)kout;                   // id == ga * R + i: one coalesced byte per lane
+            }
         }
     }
 }

@@ -83,8 +83,8 @@ def test_census_2000_steps_every_bit(name):
         assert (g["agents_alive"] == np.array([o["agents_alive"] for o, _, _, _ in outs])).all() and (g["step"] == np.array([o["step"] for o, _, _, _ in outs])).all()
         # lidar hit indices: obs[31+i] = float(4k) * (1/250) is injective in k, so the reference's k is read back from its obs
         # (all egos stay alive in these configs); every 40th step the reference's distance vectors are compared directly as well
-        k_ref = np.rint(want_obs[:, :, 31:31 + R].astype(np.float64) * 250.0 / 4.0).astype(np.int64)
-        k_ref[k_ref > 62] = 0
+        d_ref = want_obs[:, :, 31:31 + R].astype(np.float64) * 250.0          # 4k for a hit at sample k <= 62, 250 for none
+        k_ref = np.where(d_ref > 249.0, 0, np.rint(d_ref / 4.0)).astype(np.int64)
         assert (g["lidar_hit"][:, :, :R].astype(np.int64) == k_ref).all(), (name, "lidar hit index", t)
         if explicit:
             for e, (_, _, _, lid) in enumerate(outs):

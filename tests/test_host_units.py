@@ -153,3 +153,33 @@ def test_neighbor_sort_heap_fallback_against_adversary():
             assert nh == nq
             fell_back += nh > 0
     assert fell_back > 0
+
+
+def test_host_obs_row_expander_matches_the_device_formula():
+    """isx_expand_obs_rows (the host half of the compact obs transport of isx_step_host): rows rebuilt from 32-float records
+    + u8 hit indices must equal what k_lidar_obs writes: obs[31+i] = float(4k) * (1/250), k = 0 -> 250 * (1/250); columns
+    behind the last beam 0; dead ego -> all-zero row.  Every alignment of the destination, every tail length."""
+    import ctypes as C
+    from marl_traffic_intersection_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(0)
+    inv = np.float32(1.0) / np.float32(250.0)
+    for R in (72, 96, 33, 1):
+        for n in (0, 1, 7, 8, 9, 64, 1001):
+            rec = rng.normal(size=(n, 32)).astype(np.float32)
+            alive = rng.random(n) > 0.2
+            rec[:, 31] = alive
+            hits = rng.integers(0, 63, size=(n, R)).astype(np.uint8)
+            hits[rng.random((n, R)) < 0.4] = 0
+            want = np.zeros((n, 127), np.float32)
+            want[:, :31] = rec[:, :31]
+            lid = (4 * hits.astype(np.int32)).astype(np.float32) * inv
+            lid[hits == 0] = np.float32(250.0) * inv
+            want[:, 31:31 + R] = lid
+            want[~alive] = 0.0
+            for off in (0, 1, 3, 5):                          # destination misaligned by off floats
+                buf = np.full(n * 127 + 16, np.float32(np.nan))
+                dst = buf[off:off + n * 127]
+                assert lib.isx_expand_obs_rows(rec.ctypes.data, hits.ctypes.data, R, dst.ctypes.data, n) == 0
+                assert (dst.view(np.uint32) == want.reshape(-1).view(np.uint32)).all(), (R, n, off)
+                assert np.isnan(buf[:off]).all() and np.isnan(buf[off + n * 127:]).all()

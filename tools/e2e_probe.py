@@ -59,7 +59,9 @@ def main():
     for i in range(n):
         k0, k1, c0, c1 = (ms[4 * i + j] * 1e3 for j in range(4))
         print(f"  range {i}: kernels {k0:7.1f} -> {k1:7.1f} us   copy {c0:7.1f} -> {c1:7.1f} us")
-    print(f"step_host: {t * 1e6:.1f} us/step  -> {E * N / t:.3e} agent-steps/s;  obs D2H floor at the 1/1 rate above: see first line")
+    io = env.host_step_bytes()
+    print(f"step_host: {t * 1e6:.1f} us/step  -> {E * N / t:.3e} agent-steps/s;  D2H {io['d2h'] / 1e6:.1f} MB/step, {io['host_expand_threads']} host threads, "
+          f"{io['pipeline_ranges']} ranges")
 
 
 if __name__ == "__main__":
