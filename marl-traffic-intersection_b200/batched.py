@@ -231,12 +231,19 @@ class BatchedIntersectionEnv:
     def step_host(self, actions: Optional[np.ndarray], dt: float = 1.0 / 60.0, copy: bool = False):
         """The same step through HOST buffers (what env.py's list<->numpy conversions amount to): host actions in, host
         obs / reward / done / status / terminated / truncated out.  The returned arrays are views of the library's pinned
-        staging buffers, overwritten by the next host step (copy=True detaches them).  Device->host copies are pipelined
-        behind the kernels shard by shard (isx_step_pinned)."""
+        staging buffers, overwritten by the next host step (copy=True detaches them).  Over PCIe travels a compact record per
+        agent (31 features + lidar hit indices); the library's host threads rebuild the float32 rows bit-identically while
+        later env ranges are still being simulated and copied (isx_host_step_info / host_step_bytes())."""
         hv = self._host_views()
-        if actions is not None:                        # None: the caller already wrote this step's actions into host_actions
-            np.copyto(hv["actions"], np.asarray(actions, dtype=np.float32).reshape(hv["actions"].shape))
-        _lib.check(self._lib, self._lib.isx_step_pinned(self._h, C.c_float(dt), self._stream()))
+        if actions is None:                            # the caller already wrote this step's actions into host_actions
+            _lib.check(self._lib, self._lib.isx_step_pinned(self._h, C.c_float(dt), self._stream()))
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32)
+            if a.size != hv["actions"].size:
+                raise ValueError(f"Expected actions shape {hv['actions'].shape}, got {a.shape}")
+            # isx_step_host stages the actions with the library's host threads; NULL outputs = results stay in the pinned views
+            _lib.check(self._lib, self._lib.isx_step_host(self._h, C.c_void_p(a.ctypes.data), C.c_float(dt), None, None, None, None, None, None,
+                                                         self._stream()))
         out = (hv["obs"], hv["reward"], hv["done"], hv["status"], hv["terminated"].astype(bool), hv["truncated"].astype(bool))
         if copy:
             out = tuple(np.array(x) for x in out)

@@ -60,35 +60,46 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ---- host threads that complete the obs rows of a host-buffer step (isx_host_expand.cpp) while later env ranges are still
-// being simulated / copied.  Worker w owns a fixed slice of every pipeline range; a range becomes available when the host
-// callback queued behind its device->host copies fires.  No queues, no locks on the data path.
+// being simulated / copied.  The batch is cut into copy CHUNKS; behind the device->host copies of a chunk the copy stream
+// writes the step's sequence number into the chunk's flag word in pinned host memory (a 4-byte device->host copy: same
+// stream, so it lands after the data).  Worker w owns a fixed slice of every chunk and polls the flag — no driver callback
+// thread, no queues, no locks on the data path.
 struct ExpandPool {
-    struct Range { size_t a0, a1; };                 // agent range of one pipeline piece
+    struct Range { size_t a0, a1; };                 // agent range of one copy chunk
     std::vector<std::thread> threads;
     std::vector<Range> ranges;
     std::mutex mu;
     std::condition_variable cv_start, cv_done;
-    std::atomic<uint64_t> seq{0};                    // step sequence number, bumped by the caller to start a step
-    std::atomic<uint64_t> ready[64];                 // ready[c] == seq once range c's compact records are in host memory
+    uint32_t seq = 0;                                // step sequence number (guarded by mu), bumped by the caller to start a step
+    volatile uint32_t* flag = nullptr;               // pinned [chunks]: flag[c] == seq once chunk c's compact records are in host memory
     int done = 0;
     bool quit = false;
     // the job of the current step
     const float* rec = nullptr; const uint8_t* hits = nullptr; float* dst = nullptr; int R = 0;
 
     void worker(int w, int T) {
-        uint64_t seen = 0;
+        uint32_t seen = 0, cp_seen = 0;
         for (;;) {
+            bool do_copy = false;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv_start.wait(lk, [&] { return quit || seq.load() != seen; });
+                cv_start.wait(lk, [&] { return quit || seq != seen || cp_seq != cp_seen; });
                 if (quit) return;
-                seen = seq.load();
+                if (cp_seq != cp_seen) { cp_seen = cp_seq; do_copy = true; } else seen = seq;
+            }
+            if (do_copy) {
+                const size_t per = ((cp_bytes / (size_t)T) + 63) & ~(size_t)63, b0 = per * (size_t)w, b1 = b0 + per < cp_bytes ? b0 + per : cp_bytes;
+                if (b0 < cp_bytes) std::memcpy(cp_to + b0, cp_from + b0, (w == T - 1 ? cp_bytes : b1) - b0);
+                std::lock_guard<std::mutex> lk(mu);
+                if (++done == T) cv_done.notify_one();
+                continue;
             }
             for (size_t c = 0; c < ranges.size(); ++c) {
                 int spins = 0;
-                while (ready[c].load(std::memory_order_acquire) < seen) {
-                    if (++spins < 4096) __builtin_ia32_pause(); else { std::this_thread::yield(); spins = 0; }
+                while (flag[c] != seen) {              // brief pauses, then give the core away: the caller's thread must keep running
+                    if (++spins < 256) __builtin_ia32_pause(); else { std::this_thread::yield(); spins = 0; }
                 }
+                std::atomic_thread_fence(std::memory_order_acquire);
                 // slices are cut at multiples of 8 rows so that each starts 32-byte aligned (non-temporal store path)
                 const size_t n = ranges[c].a1 - ranges[c].a0, blocks = (n + 7) / 8;
                 const size_t b0 = blocks * (size_t)w / (size_t)T, b1 = blocks * (size_t)(w + 1) / (size_t)T;
@@ -102,15 +113,28 @@ struct ExpandPool {
         }
     }
     void start(int T) {
-        for (auto& r : ready) r.store(0);
         for (int w = 0; w < T; ++w) threads.emplace_back([this, w, T] { worker(w, T); });
     }
-    void begin_step(const float* rec_, const uint8_t* hits_, float* dst_, int R_) {
+    uint32_t begin_step(const float* rec_, const uint8_t* hits_, float* dst_, int R_) {
         std::lock_guard<std::mutex> lk(mu);
-        rec = rec_; hits = hits_; dst = dst_; R = R_; done = 0; seq.fetch_add(1);
+        rec = rec_; hits = hits_; dst = dst_; R = R_; done = 0; ++seq;
+        if (seq == 0) ++seq;
         cv_start.notify_all();
+        return seq;
     }
-    void release_all() { for (auto& r : ready) r.store(seq.load(), std::memory_order_release); }   // error path: let the workers finish
+    // a plain parallel memcpy on the same threads (stages the caller's actions into the pinned upload buffer)
+    void copy(void* to, const void* from, size_t bytes) {
+        const size_t T = threads.size();
+        if (T < 2 || bytes < (1u << 20)) { std::memcpy(to, from, bytes); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            cp_to = static_cast<char*>(to); cp_from = static_cast<const char*>(from); cp_bytes = bytes; done = 0; ++cp_seq;
+            cv_start.notify_all();
+        }
+        wait_step();
+    }
+    char* cp_to = nullptr; const char* cp_from = nullptr; size_t cp_bytes = 0; uint32_t cp_seq = 0;
+    void release_all() { for (size_t c = 0; c < ranges.size(); ++c) flag[c] = seq; }   // error path: let the workers finish
     void wait_step() {
         std::unique_lock<std::mutex> lk(mu);
         cv_done.wait(lk, [&] { return done == (int)threads.size(); });
@@ -121,11 +145,6 @@ struct ExpandPool {
         threads.clear();
     }
 };
-struct ExpandSignal { ExpandPool* pool; int range; };
-static void CUDART_CB expand_range_ready(void* p) {
-    ExpandSignal* s = static_cast<ExpandSignal*>(p);
-    s->pool->ready[s->range].store(s->pool->seq.load(), std::memory_order_release);   // seq is stable while a step is in flight
-}
 
 struct isx_handle {
     // One homogeneous slice of the batch (isx_create_groups): its own settings / tables over an env range of the buffers.
@@ -148,7 +167,10 @@ struct isx_handle {
     float* h_obs = nullptr; float* h_reward = nullptr;
     float* h_rec = nullptr; uint8_t* h_hitc = nullptr;   // pinned landing zone of the compact obs records (isx_host_expand.cpp)
     ExpandPool* pool = nullptr;                          // null: rows are completed inline after the step (small batches)
-    std::vector<ExpandSignal> signals;
+    struct Chunk { int piece; size_t a0, a1; };          // copy chunk: agent range [a0, a1) of the whole batch, inside pipeline piece `piece`
+    std::vector<Chunk> chunks;
+    uint32_t* h_seq = nullptr;                           // pinned: [0] = this step's sequence number, [1 + c] = flag of chunk c
+    uint32_t* d_seq = nullptr;
     float* expand_dst = nullptr;                         // where this step's rows go (h_obs or the caller's buffer)
     int host_threads = 0;
     uint8_t *h_done = nullptr, *h_status = nullptr, *h_term = nullptr, *h_trunc = nullptr;   // views into h_small
@@ -476,7 +498,9 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         // (ISX_PIPE_PLAN="w0,w1,..." (<= 16 weights) overrides, for tuning).  Several groups:
         // every group is one range.
         if (n_groups == 1) {
-            int w[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, nw = d.E >= 32768 ? 8 : d.E >= 1024 ? 4 : 1;   // 65536 envs: 5379 us with 4 ranges, 5118 with 8
+            // 65,536 envs (compact transport, 12 host threads): 1,2,3,4,6 -> 3.33 ms; 4 equal 3.59; 8 equal 3.57; 1,2,2,3 3.44
+            int w[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, nw = d.E >= 32768 ? 5 : d.E >= 1024 ? 4 : 1;
+            if (d.E >= 32768) { w[0] = 1; w[1] = 2; w[2] = 3; w[3] = 4; w[4] = 6; }   // a small first range starts the copy engine early
             if (const char* plan = getenv("ISX_PIPE_PLAN")) {
                 int k = 0;
                 for (const char* c = plan; *c && k < 16;) {
@@ -506,19 +530,35 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         cpu_set_t cs;
         if (sched_getaffinity(0, sizeof cs, &cs) == 0) T = CPU_COUNT(&cs);
         if (T < 1) T = (int)std::thread::hardware_concurrency();
+        T = T >= 4 ? (T * 3) / 4 : T;      // leave cores to the caller's thread and the driver (16 CPUs: 12 -> 3.42 ms, 14 -> 3.76, 8 -> 3.69)
         if (T > 32) T = 32;
         if (const char* ht = getenv("ISX_HOST_THREADS")) { const int v = atoi(ht); if (v >= 0 && v <= 256) T = v; }
-        if (EN < 4096 || h->pipe.size() > 64) T = 0;
-        h->host_threads = T;
-        if (T > 0) {
-            h->pool = new ExpandPool();
-            h->signals.resize(h->pipe.size());
+        if (EN < 4096) T = 0;
+        // copy chunks: every pipeline piece is drained in `sub` chunks so that the host threads start on a piece while its
+        // tail is still crossing PCIe (ISX_PIPE_CHUNKS overrides; about 1M compact-record bytes per chunk at the least)
+        {
+            int sub = 4;
+            if (const char* pcs = getenv("ISX_PIPE_CHUNKS")) { const int v = atoi(pcs); if (v >= 1 && v <= 16) sub = v; }
             for (size_t c = 0; c < h->pipe.size(); ++c) {
                 const isx_handle::Piece& pc = h->pipe[c];
-                const size_t a0 = (size_t)(h->groups[(size_t)pc.group].first + pc.e0) * d.N;
-                h->pool->ranges.push_back(ExpandPool::Range{a0, a0 + (size_t)pc.cnt * d.N});
-                h->signals[c] = ExpandSignal{h->pool, (int)c};
+                const size_t a0 = (size_t)(h->groups[(size_t)pc.group].first + pc.e0) * d.N, n = (size_t)pc.cnt * d.N;
+                int k = sub;
+                while (k > 1 && n / (size_t)k < 4096) --k;
+                for (int i = 0; i < k; ++i) {
+                    const size_t b0 = (n * (size_t)i / (size_t)k) & ~(size_t)7, b1 = i + 1 == k ? n : ((n * (size_t)(i + 1) / (size_t)k) & ~(size_t)7);
+                    if (b1 > b0) h->chunks.push_back(isx_handle::Chunk{(int)c, a0 + b0, a0 + b1});
+                }
             }
+            if (h->chunks.size() > 256) T = 0;
+        }
+        h->host_threads = T;
+        if (cudaMallocHost((void**)&h->h_seq, sizeof(uint32_t) * (h->chunks.size() + 1)) != cudaSuccess) { isx_destroy(h); return fail(ISX_E_CUDA, "pinned host allocation failed"); }
+        std::memset(h->h_seq, 0, sizeof(uint32_t) * (h->chunks.size() + 1));
+        { int rc_ = dev_alloc(h, &h->d_seq, 1); if (rc_) { isx_destroy(h); return rc_; } }
+        if (T > 0) {
+            h->pool = new ExpandPool();
+            h->pool->flag = h->h_seq + 1;
+            for (const auto& ch : h->chunks) h->pool->ranges.push_back(ExpandPool::Range{ch.a0, ch.a1});
             h->pool->start(T);
         }
     }
@@ -555,6 +595,7 @@ int isx_destroy(isx_handle* h) {
     if (h->h_small) cudaFreeHost(h->h_small);
     if (h->h_rec) cudaFreeHost(h->h_rec);
     if (h->h_hitc) cudaFreeHost(h->h_hitc);
+    if (h->h_seq) cudaFreeHost(h->h_seq);
     delete h;
     return ISX_OK;
 }
@@ -678,6 +719,8 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::ve
     if (tl) CK(cudaEventRecord((*tl)[0], st));
     const size_t EN = (size_t)d.E * d.N;
     CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * EN * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_seq, h->h_seq, sizeof(uint32_t), cudaMemcpyHostToDevice, st));      // this step's sequence number
+    size_t next_chunk = 0;
     for (size_t c = 0; c < h->pipe.size(); ++c) {
         const isx_handle::Piece& pc = h->pipe[c];
         isx_handle::Group& grp = h->groups[(size_t)pc.group];
@@ -691,10 +734,16 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::ve
         CK(cudaEventRecord(h->ev_shard[c], st));
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_shard[c], 0));
         if (tl) CK(cudaEventRecord((*tl)[3 + 4 * c], h->copy_stream));
-        // the compact obs record of the range (32 floats + R bytes per agent instead of 127 floats); host threads rebuild the rows
-        CK(cudaMemcpyAsync(h->h_rec + aoff * 32, d.obs_c + aoff * 32, sizeof(float) * an * 32, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaMemcpyAsync(h->h_hitc + aoff * (size_t)d.R, d.hit_c + aoff * (size_t)d.R, an * (size_t)d.R, cudaMemcpyDeviceToHost, h->copy_stream));
-        if (h->pool) CK(cudaLaunchHostFunc(h->copy_stream, expand_range_ready, &h->signals[c]));
+        // the compact obs records of the range (32 floats + R bytes per agent instead of 127 floats), chunk by chunk, each
+        // followed by its flag word; host threads rebuild the rows of a chunk as soon as its flag shows this step's number
+        (void)an;
+        for (; next_chunk < h->chunks.size() && h->chunks[next_chunk].piece == (int)c; ++next_chunk) {
+            const isx_handle::Chunk& ch = h->chunks[next_chunk];
+            const size_t n = ch.a1 - ch.a0;
+            CK(cudaMemcpyAsync(h->h_rec + ch.a0 * 32, d.obs_c + ch.a0 * 32, sizeof(float) * n * 32, cudaMemcpyDeviceToHost, h->copy_stream));
+            CK(cudaMemcpyAsync(h->h_hitc + ch.a0 * (size_t)d.R, d.hit_c + ch.a0 * (size_t)d.R, n * (size_t)d.R, cudaMemcpyDeviceToHost, h->copy_stream));
+            CK(cudaMemcpyAsync(h->h_seq + 1 + next_chunk, h->d_seq, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+        }
         if (tl) CK(cudaEventRecord((*tl)[4 + 4 * c], h->copy_stream));
     }
     // the stream order of copy_stream puts this after the last shard's kernels (its wait on ev_shard[last])
@@ -714,7 +763,7 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::ve
 // One host-buffer step whose obs rows land in `dst` ([E*N][127] floats in host memory).  Synchronous.
 static int host_step_into(isx_handle* h, float dt, cudaStream_t st, float* dst, std::vector<cudaEvent_t>* tl = nullptr) {
     CK(cudaSetDevice(h->device));
-    if (h->pool) h->pool->begin_step(h->h_rec, h->h_hitc, dst, h->d.R);
+    if (h->pool) h->h_seq[0] = h->pool->begin_step(h->h_rec, h->h_hitc, dst, h->d.R);
     auto run = [&]() -> int {
         if (!h->use_graph || tl) {
             const int rc = enqueue_pinned_step(h, dt, st, tl);
@@ -818,7 +867,7 @@ int isx_step_host(isx_handle* h, const float* actions, float dt, float* obs, flo
     if (!actions) return fail(ISX_E_ARG, "actions is null");
     const Dev& d = h->d;
     const size_t EN = (size_t)d.E * d.N, E = (size_t)d.E;
-    std::memcpy(h->h_actions, actions, sizeof(float) * EN * 2);
+    if (h->pool) h->pool->copy(h->h_actions, actions, sizeof(float) * EN * 2); else std::memcpy(h->h_actions, actions, sizeof(float) * EN * 2);
     // the obs rows are completed straight into the caller's buffer (no staging copy of 127 floats per agent)
     const int rc = host_step_into(h, dt, static_cast<cudaStream_t>(stream), obs ? obs : h->h_obs);
     if (rc) return rc;

@@ -395,6 +395,59 @@ class OracleEnv(_EnvBase):
     _prefix = "isxo_"
 
 
+def step_batch(envs, actions, dt=1.0 / 60.0, lidar=False, npc_cap=0, threads=0):
+    """Steps a list of RefEnv objects with ONE library call on `threads` host threads (isxref_step_batch) and returns dense
+    arrays over the env index: obs [E,N,127], reward, done, status [E,N], terminated, truncated, agents_alive, step [E],
+    events [E] (EVENTS_DTYPE), optionally lidar_k [E,N,96] (hit sample index, 0 = none) and npc_pose [E,npc_cap,4]."""
+    lib = _load(REF_SO, "isxref_")
+    f = lib.isxref_step_batch
+    f.restype = None
+    f.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float] + [C.c_void_p] * 11 + [C.c_int, C.c_int]
+    E, N = len(envs), envs[0].n
+    a = np.ascontiguousarray(actions, np.float32).reshape(E, N, 2)
+    hs = (C.c_void_p * E)(*[e._h for e in envs])
+    out = dict(obs=np.zeros((E, N, OBS_DIM), np.float32), reward=np.zeros((E, N), np.float32), done=np.zeros((E, N), np.int32),
+               status=np.zeros((E, N), np.int32), terminated=np.zeros(E, np.int32), truncated=np.zeros(E, np.int32),
+               agents_alive=np.zeros(E, np.int32), step=np.zeros(E, np.int32), events=np.zeros(E, EVENTS_DTYPE))
+    lk = np.zeros((E, N, 96), np.uint8) if lidar else None
+    pose = np.zeros((E, max(npc_cap, 1), 4), np.float32) if npc_cap > 0 else None
+    f(hs, E, _fp(a), N, np.float32(dt), out["obs"].ctypes.data, out["reward"].ctypes.data, out["done"].ctypes.data,
+      out["status"].ctypes.data, out["terminated"].ctypes.data, out["truncated"].ctypes.data, out["agents_alive"].ctypes.data,
+      out["step"].ctypes.data, out["events"].ctypes.data, lk.ctypes.data if lidar else None, pose.ctypes.data if pose is not None else None,
+      int(npc_cap), int(threads or os.cpu_count() or 1))
+    if lidar:
+        out["lidar_k"] = lk
+    if pose is not None:
+        out["npc_pose"] = pose
+    return out
+
+
+def philox_actions_batch(seeds, env_ids, ticks, n_agents: int) -> np.ndarray:
+    """philox_actions for many envs at once: seeds / env_ids / ticks are length-E sequences -> [E, n_agents, 2]."""
+    E = len(env_ids)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    env = np.repeat(np.asarray(env_ids, np.uint32), n_agents)
+    tick = np.repeat(np.asarray(ticks, np.uint32), n_agents)
+    seeds = np.asarray(seeds, np.uint64)
+    k0 = np.repeat((seeds & np.uint64(0xFFFFFFFF)).astype(np.uint32), n_agents)
+    k1 = np.repeat((seeds >> np.uint64(32)).astype(np.uint32), n_agents)
+    c = [env, tick, np.tile(np.arange(n_agents, dtype=np.uint32), E), np.full(E * n_agents, 0x41435431, np.uint32)]
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c[0].astype(np.uint64)
+            p1 = M1 * c[2].astype(np.uint64)
+            n0 = (p1 >> np.uint64(32)).astype(np.uint32) ^ c[1] ^ k0
+            n1 = p1.astype(np.uint32)
+            n2 = (p0 >> np.uint64(32)).astype(np.uint32) ^ c[3] ^ k1
+            n3 = p0.astype(np.uint32)
+            c = [n0, n1, n2, n3]
+            k0 = k0 + np.uint32(0x9E3779B9)
+            k1 = k1 + np.uint32(0xBB67AE85)
+    thr = (c[0] >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 8388608.0) - np.float32(1.0)
+    st = (c[1] >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 8388608.0) - np.float32(1.0)
+    return np.stack([thr, st], axis=1).reshape(E, n_agents, 2)
+
+
 def unit_of(path: str, prefix: str) -> _Unit:
     """Unit-probe view of any library exporting the <prefix>route / on_road / lidar ... subset."""
     return _Unit(_load(path, prefix), prefix)

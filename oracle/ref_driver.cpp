@@ -14,6 +14,8 @@
 #include "IntersectionEnv.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstring>
 #include <stdexcept>
 #include <map>
@@ -242,6 +244,50 @@ int isxref_step(void *h, const float *throttle, const float *steer, int n_action
 }
 
 void isxref_get_events(void *h, isx_traffic_events *ev) { *ev = static_cast<RefEnv *>(h)->ev; }
+
+/* n envs stepped by one call on `threads` host threads (the census tests compare hundreds of envs per step; one ctypes
+ * call per env and step costs more than the simulation).  All arrays are dense over the env index; N = egos per env;
+ * lidar_k[e][a][96] = hit sample index (distance / 4, 0 = none) and npc_pose[e][cap][4] = x, y, v, heading in list order
+ * are optional.  Every env steps exactly as in isxref_step (same function, same stream positioning). */
+void isxref_step_batch(void **handles, int n, const float *actions, int N, float dt, float *obs, float *reward, int32_t *done,
+                       int32_t *status, int32_t *terminated, int32_t *truncated, int32_t *agents_alive, int32_t *step,
+                       isx_traffic_events *events, uint8_t *lidar_k, float *npc_pose, int cap, int threads) {
+    if (threads < 1) threads = 1;
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        std::vector<float> th((size_t)N), st((size_t)N);
+        for (;;) {
+            const int e = next.fetch_add(1);
+            if (e >= n) return;
+            const size_t eo = (size_t)e * (size_t)N;
+            for (int a = 0; a < N; ++a) { th[(size_t)a] = actions[(eo + a) * 2]; st[(size_t)a] = actions[(eo + a) * 2 + 1]; }
+            step[e] = isxref_step(handles[e], th.data(), st.data(), N, dt, obs + eo * ISX_OBS_DIM, reward + eo, done + eo, status + eo,
+                                  terminated + e, truncated + e, agents_alive + e);
+            RefEnv *r = static_cast<RefEnv *>(handles[e]);
+            if (events) events[e] = r->ev;
+            if (lidar_k) {
+                for (int a = 0; a < N && size_t(a) < r->env.lidars.size(); ++a) {
+                    const auto &d = r->env.lidars[size_t(a)].distances;
+                    uint8_t *o = lidar_k + (eo + a) * 96;
+                    for (size_t i = 0; i < 96; ++i) o[i] = (i < d.size() && d[i] < 250.0f) ? uint8_t(d[i] / 4.0f) : uint8_t(0);
+                }
+            }
+            if (npc_pose) {
+                int k = 0;
+                for (const auto &c : r->env.traffic_cars) {
+                    if (k >= cap) break;
+                    float *o = npc_pose + ((size_t)e * cap + k) * 4;
+                    o[0] = c.state.x; o[1] = c.state.y; o[2] = c.state.v; o[3] = c.state.heading;
+                    ++k;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+}
 
 int isxref_get_egos(void *h, isx_car_state *out) {
     RefEnv *r = static_cast<RefEnv *>(h);

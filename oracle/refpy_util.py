@@ -2,7 +2,7 @@
 
 `make -C oracle pyref` leaves in oracle/_ref/ (git-ignored build outputs that travel to the GPU box):
   MARLEnv.so          the reference's pybind11 module (cpp/bindings.cpp over the unmodified sources + the RNG shim)
-  refpy/{env,utils,cpp_backend}.pyc   byte-compiled copies of the reference's env.py / utils.py / cpp_backend.py
+  refpy/{env,utils,cpp_backend}.pyc.bin   byte-compiled copies of the reference's env.py / utils.py / cpp_backend.py
 
 Only tests/ and bench.py's CPU-baseline leg import this module; the product package never does.
 
@@ -23,11 +23,11 @@ REFPY = os.path.join(REF_OUT, "refpy")
 
 
 def have_pyref() -> bool:
-    return os.path.exists(os.path.join(REF_OUT, "MARLEnv.so")) and os.path.exists(os.path.join(REFPY, "env.pyc"))
+    return os.path.exists(os.path.join(REF_OUT, "MARLEnv.so")) and os.path.exists(os.path.join(REFPY, "env.pyc.bin"))
 
 
 def _load_pyc(name: str, alias: str):
-    path = os.path.join(REFPY, name + ".pyc")
+    path = os.path.join(REFPY, name + ".pyc.bin")
     loader = importlib.machinery.SourcelessFileLoader(alias, path)
     spec = importlib.util.spec_from_loader(alias, loader)
     mod = importlib.util.module_from_spec(spec)

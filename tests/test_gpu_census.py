@@ -5,7 +5,7 @@ obs, rewards, done / status, terminated / truncated, agents_alive, step, lidar h
 NPC count and poses.  (north_star: "2000-step rollout ... identical seeds, actions and routes".)
 
 The three seeds run as three config groups of one heterogeneous batch (isx_create_groups), 192 envs per config; the CPU
-checkers step on all host cores (ctypes releases the GIL)."""
+checkers step on all host cores (isxref_step_batch: one library call per step for all envs)."""
 import os
 from concurrent.futures import ThreadPoolExecutor
 
@@ -49,67 +49,73 @@ def test_census_2000_steps_every_bit(name):
                             density=float(base.get("traffic_density", 0.5)), lidar_rays=R, seed=s, env_id=e, max_steps=2000))
             seed_of.append(s)
             id_of.append(e)
-    pool = ThreadPoolExecutor(os.cpu_count() or 4)
     obs0, _ = b.reset()
     torch.cuda.synchronize()
     assert (u32(obs0.cpu().numpy()) == u32(np.stack([r.obs() for r in refs]))).all()
     hist = np.zeros(6, np.int64)
     spawned = removed = 0
+    batch = cls is po.RefEnv                                   # one library call per step for all envs (isxref_step_batch)
+    pool = None if batch else ThreadPoolExecutor(os.cpu_count() or 4)
 
-    def one(args):
-        e, act, explicit = args
-        r = refs[e]
-        o = r.step(act)
-        ev = r.events() if traffic else None
-        npc = r.npcs() if traffic else None
-        lid = [r.lidar(a) for a in range(N)] if explicit else None
-        return o, ev, npc, lid
+    def slow_step(act):
+        """per-env ctypes path (the C port has no batch entry point): same dict as pyoracle.step_batch"""
+        def one(e):
+            r = refs[e]
+            o = r.step(act[e])
+            lk = np.zeros((N, 96), np.uint8)
+            for a in range(N):
+                d = r.lidar(a)
+                lk[a, :len(d)] = np.where(d >= 250.0, 0, d / 4.0).astype(np.uint8)
+            pose = np.zeros((M, 4), np.float32)
+            ev = r.events() if traffic else np.zeros(1, po.EVENTS_DTYPE)[0]
+            if traffic:
+                npc = r.npcs()
+                for j, f in enumerate(("x", "y", "v", "heading")):
+                    pose[:len(npc), j] = npc[f]
+            return o, lk, pose, ev
+        res = list(pool.map(one, range(E)))
+        out = {k: np.stack([o[k] for o, _, _, _ in res]) for k in ("obs", "reward", "done", "status")}
+        for k in ("terminated", "truncated", "agents_alive", "step"):
+            out[k] = np.array([int(o[k]) for o, _, _, _ in res])
+        out["lidar_k"] = np.stack([x[1] for x in res])
+        out["npc_pose"] = np.stack([x[2] for x in res])
+        out["events"] = np.array([x[3] for x in res], po.EVENTS_DTYPE)
+        return out
 
+    ticks = np.zeros(E, np.int64)
     for t in range(STEPS):
-        act = np.stack([po.philox_actions(seed_of[e], id_of[e], refs[e].tick + 1, N) for e in range(E)])
+        ticks += 1
+        act = po.philox_actions_batch(seed_of, id_of, ticks, N)
         b.step(torch.from_numpy(act).cuda())
-        explicit = (t % 40 == 0)
-        outs = list(pool.map(one, [(e, act[e], explicit) for e in range(E)]))
+        o = po.step_batch(refs, act, lidar=True, npc_cap=M if traffic else 0) if batch else slow_step(act)
         torch.cuda.synchronize()
         g = {k: b.buf[k].cpu().numpy() for k in ("obs", "reward", "done", "status", "terminated", "truncated", "agents_alive", "step", "lidar_hit")}
-        want_obs = np.stack([o["obs"] for o, _, _, _ in outs])
-        bad = u32(g["obs"]) != u32(want_obs)
+        bad = u32(g["obs"]) != u32(o["obs"])
         assert not bad.any(), (name, "obs", t, np.argwhere(bad)[:3].tolist())
-        assert (u32(g["reward"]) == u32(np.stack([o["reward"] for o, _, _, _ in outs]))).all(), (name, "reward", t)
-        assert (g["done"] == np.stack([o["done"] for o, _, _, _ in outs])).all() and (g["status"] == np.stack([o["status"] for o, _, _, _ in outs])).all(), (name, "status", t)
-        term = np.array([o["terminated"] for o, _, _, _ in outs])
-        trunc = np.array([o["truncated"] for o, _, _, _ in outs])
+        assert (u32(g["reward"]) == u32(o["reward"])).all(), (name, "reward", t)
+        assert (g["done"] == o["done"]).all() and (g["status"] == o["status"]).all(), (name, "status", t)
+        term, trunc = o["terminated"].astype(bool), o["truncated"].astype(bool)
         assert (g["terminated"].astype(bool) == term).all() and (g["truncated"].astype(bool) == trunc).all(), (name, "flags", t)
-        assert (g["agents_alive"] == np.array([o["agents_alive"] for o, _, _, _ in outs])).all() and (g["step"] == np.array([o["step"] for o, _, _, _ in outs])).all()
-        # lidar hit indices: obs[31+i] = float(4k) * (1/250) is injective in k, so the reference's k is read back from its obs
-        # (all egos stay alive in these configs); every 40th step the reference's distance vectors are compared directly as well
-        d_ref = want_obs[:, :, 31:31 + R].astype(np.float64) * 250.0          # 4k for a hit at sample k <= 62, 250 for none
-        k_ref = np.where(d_ref > 249.0, 0, np.rint(d_ref / 4.0)).astype(np.int64)
-        assert (g["lidar_hit"][:, :, :R].astype(np.int64) == k_ref).all(), (name, "lidar hit index", t)
-        if explicit:
-            for e, (_, _, _, lid) in enumerate(outs):
-                for a in range(N):
-                    k = np.where(lid[a] >= 250.0, 0, lid[a] / 4.0).astype(np.int64)
-                    assert (g["lidar_hit"][e, a, :R].astype(np.int64) == k).all(), (name, "lidar distances", t, e, a)
+        assert (g["agents_alive"] == o["agents_alive"]).all() and (g["step"] == o["step"]).all(), (name, "agents_alive/step", t)
+        # lidar hit indices, read from the reference's Lidar::distances of every ego (all egos stay alive in these configs)
+        assert (g["lidar_hit"][:, :, :R] == o["lidar_k"][:, :, :R]).all(), (name, "lidar hit index", t)
         if traffic:
-            ev = b.buf["events"].cpu().numpy()
+            ev = b.buf["events"].cpu().numpy().astype(np.int64)
+            ev[:, 3:5] &= 0xFFFFFFFF
+            want = o["events"]
+            for col, f in ((0, "rng_draws"), (1, "spawn_route"), (2, "spawned"), (3, "removed_mask"), (5, "npc_count")):
+                assert (ev[:, col] == want[f].astype(np.int64)).all(), (name, "event " + f, t)
+            if not batch:                                       # the reference driver does not infer collided_mask
+                assert (ev[:, 4] == want["collided_mask"].astype(np.int64)).all(), (name, "event collided_mask", t)
             nc = b.buf["npc_count"].cpu().numpy()
-            want_ev = np.array([[int(v["rng_draws"]), int(v["spawn_route"]), int(v["spawned"]), int(v["removed_mask"]), int(v["collided_mask"]), int(v["npc_count"])]
-                                for _, v, _, _ in outs], np.int64)
-            got_ev = ev.astype(np.int64)
-            got_ev[:, 3:5] &= 0xFFFFFFFF
-            cols = [0, 1, 2, 3, 5] if cls is po.RefEnv else [0, 1, 2, 3, 4, 5]      # the reference driver does not infer collided_mask
-            assert (got_ev[:, cols] == want_ev[:, cols]).all(), (name, "events", t)
-            assert (nc == want_ev[:, 5]).all(), (name, "npc_count", t)
-            spawned += int(want_ev[:, 2].sum())
-            removed += int(sum(bin(int(m)).count("1") for m in want_ev[:, 3]))
-            pose = {k: b.buf[k].cpu().numpy() for k in ("npc_x", "npc_y", "npc_v", "npc_heading")}
-            for e, (_, _, npc, _) in enumerate(outs):
-                n = len(npc)
-                for f, k in (("x", "npc_x"), ("y", "npc_y"), ("v", "npc_v"), ("heading", "npc_heading")):
-                    assert (u32(pose[k][e, :n]) == u32(npc[f])).all(), (name, "npc " + f, t, e)
-        for o, _, _, _ in outs:
-            hist += np.bincount(o["status"], minlength=6)
+            assert (nc == want["npc_count"]).all(), (name, "npc_count", t)
+            spawned += int(want["spawned"].sum())
+            removed += int(sum(bin(int(m)).count("1") for m in want["removed_mask"]))
+            live = np.arange(M)[None, :] < nc[:, None]
+            for j, k in enumerate(("npc_x", "npc_y", "npc_v", "npc_heading")):
+                got = b.buf[k].cpu().numpy()
+                assert (u32(got)[live] == u32(o["npc_pose"][:, :, j])[live]).all(), (name, k, t)
+        hist += np.bincount(o["status"].reshape(-1), minlength=6)
         need = term | trunc
         if need.any():
             b.reset(torch.from_numpy(need.astype(np.uint8)).cuda())
@@ -124,5 +130,6 @@ def test_census_2000_steps_every_bit(name):
         assert spawned > 100 and removed > 50
     print(f"census {name}: {E} envs x {N} agents x {STEPS} steps = {E * N * STEPS} agent-steps, checker {cls.__name__}, "
           f"0 mismatches, status histogram {dict(zip(po.STATUS_NAMES, hist.tolist()))}, npc spawned/removed {spawned}/{removed}")
-    pool.shutdown()
+    if pool is not None:
+        pool.shutdown()
     b.close()
