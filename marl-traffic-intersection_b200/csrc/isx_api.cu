@@ -389,10 +389,10 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         ALLOC(d_bits, rt.bits.size()); UPLOAD(d_bits, rt.bits.data(), sizeof(uint32_t) * rt.bits.size());
         ALLOC(d_skip, rt.skip.size()); UPLOAD(d_skip, rt.skip.data(), rt.skip.size());
         q.route_path = d_paths; q.route_meta = d_meta; q.road_bits = d_bits; q.road_skip = d_skip; q.rel_angle = d_rel;
-        q.box_lo = rt.box_lo; q.box_hi = rt.box_hi;
+        q.box_lo = rt.box_lo; q.box_hi = rt.box_hi; q.ana = rt.ana;
     }
     d.route_path = gd[0].route_path; d.route_meta = gd[0].route_meta; d.road_bits = gd[0].road_bits; d.road_skip = gd[0].road_skip;
-    d.rel_angle = d_rel; d.box_lo = gd[0].box_lo; d.box_hi = gd[0].box_hi;
+    d.rel_angle = d_rel; d.box_lo = gd[0].box_lo; d.box_hi = gd[0].box_hi; d.ana = gd[0].ana;
 
     // ---- state, scratch and output buffers, shared by all groups
     const size_t EN = (size_t)d.E * d.N, EM = (size_t)d.E * d.M, E = (size_t)d.E;
@@ -445,7 +445,7 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
             v.lanes = q.lanes; v.use_team = q.use_team; v.respawn = q.respawn; v.max_steps = q.max_steps;
             v.traffic = q.traffic; v.T = q.T; v.auto_reset = q.auto_reset; v.rc = q.rc; v.seed = q.seed; v.env_base = q.env_base;
             v.route_path = q.route_path; v.route_meta = q.route_meta; v.road_bits = q.road_bits; v.road_skip = q.road_skip;
-            v.box_lo = q.box_lo; v.box_hi = q.box_hi;
+            v.box_lo = q.box_lo; v.box_hi = q.box_hi; v.ana = q.ana;
             grp.d = v; grp.first = first;
             first += q.E;
         }

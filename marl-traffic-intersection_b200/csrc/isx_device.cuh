@@ -31,6 +31,7 @@ struct Dev {
     const uint32_t* road_bits;   // [ROAD_ROWS][ROAD_WORDS]
     const uint8_t* road_skip;    // [SKIP_DIM][SKIP_DIM]
     int box_lo, box_hi;          // strip interior [box_lo, box_hi] x [0,749] (and transpose) is all road
+    RoadAna ana;                 // analytic off-road bound of the beam march (isx_sim.cuh ray_safe_samples)
     const float* rel_angle;      // [R]
     // ---- ego state [E][N]
     float *ex, *ey, *ev, *eh, *esteer, *eacc, *epd, *epa0, *epa1;

@@ -83,8 +83,7 @@ void isxh_lidar(int lanes, int rays, const float* self_pose, const float* others
         sincosf_(h + rel[i], &s, &c);
         const Ray ray = make_ray(cx, cy, c, -s);
         bool hit;
-        const RoadView rv{t->bits.data(), t->skip.data(), t->box_lo, t->box_hi};
-        const int ke = ray_road_event(rv, ray, &hit);
+        const int ke = ray_road_event_ana(t->ana, t->bits.data(), ray, &hit);   // as k_lidar_obs marches (the skip-table march: isxh_road_events)
         int best = hit ? ke : 0;
         const int kmax = hit ? ke - 1 : ke - 1;     // cars only count strictly before the road event
         if (kmax >= 1) {
@@ -125,6 +124,25 @@ void isxh_march_stats(int lanes, int rays, int lockstep, const float* self_pose,
         k_event[i] = ray_road_event(rv, ray, &hit);
     }
 }
+// Ray-level comparison of the two road marches on n rays (origin + absolute beam angle, as Lidar.cpp:24-26 forms them):
+// skip-table / strip-box march (ray_road_event) against analytic jump + exact samples (ray_road_event_ana).  out6 per ray:
+// ke_old, hit_old, ke_new, hit_new, exact samples tested after the jump, K of the jump.
+void isxh_road_events(int lanes, int n, const float* cx, const float* cy, const float* angle, int* out6) {
+    const RoadTables* t = tables_for(lanes);
+    const RoadView rv{t->bits.data(), t->skip.data(), t->box_lo, t->box_hi};
+    for (int i = 0; i < n; ++i) {
+        float s, c;
+        sincosf_(angle[i], &s, &c);
+        const Ray ray = make_ray(cx[i], cy[i], c, -s);
+        bool h0, h1;
+        int tests = 0;
+        const int k0 = ray_road_event(rv, ray, &h0);
+        const int k1 = ray_road_event_ana(t->ana, t->bits.data(), ray, &h1, &tests);
+        int* o = out6 + 6 * (size_t)i;
+        o[0] = k0; o[1] = h0; o[2] = k1; o[3] = h1; o[4] = tests; o[5] = ray_safe_samples(t->ana, ray);
+    }
+}
+int isxh_ana_enabled(int lanes) { return tables_for(lanes)->ana.enabled; }
 int isxh_self_status(int lanes, float x, float y, float h, float gx, float gy, float px, float py) {
     return ego_self_status(lanes, x, y, h, F2{gx, gy}, F2{px, py});
 }

@@ -375,6 +375,79 @@ ISX_HD int ray_road_event(const RoadView& rv, const Ray& r, bool* hit) {
     return m.ke;
 }
 
+// ---- analytic lower bound of the first road event (exactness-preserving; replaces the strip boxes and the first skip steps)
+// RoadGeometry::is_on_road is "two strips U four corner squares minus four grass discs": its complement is, per screen
+// quadrant, the Minkowski sum of the quarter plane {sx(x-C) >= U, sy(y-C) >= U} (U = lanes*42 + 84) with a disc of radius
+// 84 — two straight walls joined by a quarter circle.  An off-road PIXEL therefore lies within 84 of one of the four
+// quarter planes (checked pixel by pixel when the tables are built, isx_tables.h), and the real sample position lies within
+// (1,1) of its pixel, so no sample whose real position is farther than rho = 84 + 1.5 from all four quarter planes can be a
+// road event.  ray_safe_samples returns K such that samples 1..K are certainly not road events; the samples after K are
+// then tested with the exact pixel arithmetic, one by one.  Off-screen samples need no bound: a ray that leaves the screen
+// never comes back, reports "no hit" (Lidar.cpp:38-40), and cars are only ever tested against on-screen pixels.
+//   x side: tR / tL = time at which the ray is inside the half plane a >= g / a <= -g (a = x - C, g = U - rho), inf if never;
+//   same for y; the blob (quadrant) entered first is (earlier x side, earlier y side) at ts = max of the two times —
+//   always a lower bound of the true entry.  If the ray is, at ts, in the notch between the two walls and the quarter
+//   circle, the bound is refined with the circle (one square root); the other three blobs are bounded by their slab times.
+// Only bounds: approximate reciprocal / square root and explicit FMAs are fine (0.08 px of slack against ~1e-4 px of error).
+struct RoadAna { float g, U, rho2; int enabled; };
+ISX_HD float approx_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+ISX_HD float slab_time(float a, float d, float inv_d, float g) {           // first t >= 0 with a + d t >= g
+    return (a >= g) ? 0.0f : ((d > 0.0f) ? (g - a) * inv_d : INFINITY);
+}
+ISX_HD int ray_safe_samples(const RoadAna& ra, const Ray& r) {
+    const float a = r.cx - (float)ROAD_HALF, b = r.cy - (float)ROAD_HALF;
+    const float tR = slab_time(a, r.dx, r.inv_dx, ra.g), tL = slab_time(-a, -r.dx, -r.inv_dx, ra.g);
+    const float tD = slab_time(b, r.dy, r.inv_dy, ra.g), tU = slab_time(-b, -r.dy, -r.inv_dy, ra.g);
+    const bool right = tR <= tL, down = tD <= tU;
+    const float tx = right ? tR : tL, txo = right ? tL : tR;
+    const float ty = down ? tD : tU, tyo = down ? tU : tD;
+    const float ts = fmaxf(tx, ty);
+    const float t2 = fminf(fmaxf(txo, ty), fmaxf(tx, tyo));                // earliest slab time of the other three blobs
+    float entry = ts;
+    if (ts < 1000.0f) {
+        const float w1 = (right ? a : -a) - ra.U, w2 = (down ? b : -b) - ra.U;
+        const float d1 = right ? r.dx : -r.dx, d2 = down ? r.dy : -r.dy;
+        const float p1 = fmaf(d1, ts, w1), p2 = fmaf(d2, ts, w2);
+        if (p1 < -1e-3f && p2 < -1e-3f) {                                  // in the notch: only the quarter circle can be hit
+            const float B = fmaf(w1, d1, w2 * d2);
+            const float Cq = fmaf(w1, w1, fmaf(w2, w2, -ra.rho2));
+            const float D = fmaf(B, B, -Cq);
+            entry = (D < -0.05f) ? INFINITY : fmaxf(ts, -B - approx_sqrt(fmaxf(D, 0.0f)));
+        }
+    }
+    entry = fminf(fminf(entry, t2), 1000.0f);
+    const int k = (int)floorf((entry - 0.01f) * 0.25f);
+    return !ra.enabled ? 0 : (k < 0 ? 0 : (k > LIDAR_MAX_K ? LIDAR_MAX_K : k));
+}
+
+// One exact step of the march after the analytic jump: the next sample (plus what the skip table of the last TESTED pixel
+// allows, when there is one) is tested with the exact arithmetic of Lidar.cpp:34-46.
+ISX_HD void march_next(const uint32_t* bits, const Ray& r, March& m) {
+    m.k += 1;
+    if (m.k > LIDAR_MAX_K) { m.ke = LIDAR_MAX_K + 1; m.done = true; return; }
+    const int e = sample_event(bits, r, m.k, m.px, m.py);
+    if (e) { m.ke = m.k; m.hit = (e == 2); m.done = true; }
+}
+// Road event of one ray, sequential form of what the kernel does (analytic jump, then exact samples).
+ISX_HD int ray_road_event_ana(const RoadAna& ra, const uint32_t* bits, const Ray& r, bool* hit, int* tests = nullptr) {
+    March m;
+    march_init(r, m);
+    int n = 0;
+    if (!m.done) m.k = ray_safe_samples(ra, r);
+    while (!m.done) { march_next(bits, r, m); ++n; }
+    if (tests) *tests = n;
+    *hit = m.hit;
+    return m.ke;
+}
+
 // First sample k in [1, kmax] whose pixel lies inside the rectangle, or 0.  A slab test in real arithmetic
 // (0.01 px slack, >100x the float rounding of the sample positions) brackets the candidate k range; the
 // candidates are then checked with the exact integer test, in order.  Only on-screen pixels can be hit
@@ -405,8 +478,10 @@ ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
         } else if (lo > 0.01f || hi < -0.01f) return 0;
     }
     if (!(t0 <= t1)) return 0;
-    int ka = (int)floorf(t0 * 0.25f - 0.01f);      // one early is harmless: candidates are verified
-    int kb = (int)ceilf(t1 * 0.25f + 0.01f);
+    // a sample inside the rectangle sits at least 0.0099 px inside the slab bounds (their 0.01 px of slack minus the
+    // rounding of the sample position), so 4k lies strictly inside [t0, t1]: no extra candidate on either side
+    int ka = (int)ceilf(t0 * 0.25f);
+    int kb = (int)floorf(t1 * 0.25f);
     if (ka < 1) ka = 1;
     if (kb > kmax) kb = kmax;
     for (int k = ka; k <= kb; ++k) {

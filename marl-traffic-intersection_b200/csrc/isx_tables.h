@@ -140,6 +140,7 @@ struct RoadTables {
     std::vector<uint32_t> bits;   // ROAD_ROWS x ROAD_WORDS
     std::vector<uint8_t> skip;    // SKIP_DIM x SKIP_DIM
     int box_lo = 1, box_hi = 0;   // every pixel of [box_lo, box_hi] x [0,749] and of its transpose is road (empty if lo > hi)
+    RoadAna ana{0.0f, 0.0f, 0.0f, 0};   // analytic off-road bound (ray_safe_samples); enabled only if verified below
 };
 
 // Builds the folded bitmap and skip table from on_road() evaluated at every integer pixel, exactly as the
@@ -183,6 +184,21 @@ inline bool build_road_tables(int lanes, RoadTables* t) {
         for (int y = 0; ok && y < H; ++y)
             for (int x = lo; ok && x <= hi; ++x) ok = road[(size_t)y * W + x] && road[(size_t)x * W + y];
         if (ok) { t->box_lo = lo; t->box_hi = hi; } else { t->box_lo = 1; t->box_hi = 0; }
+    }
+    // analytic bound (isx_sim.cuh ray_safe_samples): every off-road pixel must lie within CORNER_RADIUS of one of the four
+    // quarter planes {sx (x - 375) >= U, sy (y - 375) >= U}; checked here for every pixel of the screen, in double.
+    {
+        const double U = (double)lanes * LANE_WIDTH_PX + CORNER_RADIUS, cr = CORNER_RADIUS;
+        bool ok = (double)lanes * LANE_WIDTH_PX - 1.5 > 0.0;
+        for (int y = 0; ok && y < H; ++y)
+            for (int x = 0; ok && x < W; ++x) {
+                if (road[(size_t)y * W + x]) continue;
+                const double a = std::fabs((double)x - ROAD_HALF), b = std::fabs((double)y - ROAD_HALF);   // nearest quarter plane = own quadrant
+                const double e1 = std::max(U - a, 0.0), e2 = std::max(U - b, 0.0);
+                ok = std::sqrt(e1 * e1 + e2 * e2) <= cr + 1e-6;
+            }
+        const float rho = CORNER_RADIUS + 1.5f;
+        t->ana = RoadAna{(float)lanes * LANE_WIDTH_PX - 1.5f, (float)lanes * LANE_WIDTH_PX + CORNER_RADIUS, rho * rho, ok ? 1 : 0};
     }
     t->bits.assign((size_t)ROAD_ROWS * ROAD_WORDS, 0u);
     std::vector<int> fclr((size_t)ROAD_ROWS * ROAD_ROWS, BIG);

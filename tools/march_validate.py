@@ -1,0 +1,48 @@
+import ctypes as C, numpy as np, sys, time
+lib = C.CDLL("/root/repo/marl-traffic-intersection_b200/csrc/libisx_host_units.so")
+def run(L, cx, cy, ang):
+    n = len(cx)
+    out = np.zeros((n, 6), np.int32)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    cx, cy, ang = f(cx), f(cy), f(ang)
+    lib.isxh_road_events(L, n, cx.ctypes.data_as(C.c_void_p), cy.ctypes.data_as(C.c_void_p), ang.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+N = int(float(sys.argv[2])) if len(sys.argv) > 2 else 2_000_000
+for L in (1, 2, 3, 4):
+    assert lib.isxh_ana_enabled(L) == 1, L
+    rw = 42 * L; U = rw + 84
+    sets = {}
+    sets["uniform"] = (rng.uniform(-30, 780, N), rng.uniform(-30, 780, N), rng.uniform(-7, 7, N))
+    # integer / half-integer origins, axis-aligned and near-axis directions
+    ax = rng.choice([0, np.pi/2, np.pi, -np.pi/2, -np.pi, 2*np.pi], N) + rng.choice([0, 1e-7, -1e-7, 1e-4, -1e-4, 1e-2, -1e-2], N)
+    sets["axis"] = (rng.integers(0, 750, N).astype(float) + rng.choice([0, .5, .999, .001], N), rng.integers(0, 750, N).astype(float) + rng.choice([0, .5, .999, .001], N), ax)
+    # origins hugging the walls: x at 375 +- rw +- small, or on the arc radius 84 +- small around the disc centres
+    side = rng.choice([-1, 1], N); eps = rng.choice([0, .01, -.01, .5, -.5, 1, -1, 1.4, -1.4, 1.6, -1.6, 3, -3], N)
+    sets["wall_x"] = (375 + side * (rw + eps), rng.uniform(0, 750, N), rng.uniform(-np.pi, np.pi, N))
+    sets["wall_y"] = (rng.uniform(0, 750, N), 375 + side * (rw + eps), rng.uniform(-np.pi, np.pi, N))
+    th = rng.uniform(0, 2*np.pi, N); rr = 84 + eps + rng.uniform(-.2, .2, N)
+    sx, sy = rng.choice([-1, 1], N), rng.choice([-1, 1], N)
+    ox, oy = 375 + sx * U + rr * np.cos(th), 375 + sy * U + rr * np.sin(th)
+    sets["arc"] = (ox, oy, rng.uniform(-np.pi, np.pi, N))
+    # tangent-ish to the arc: direction perpendicular to radius +- small
+    sets["arc_tangent"] = (ox, oy, -(th + np.pi/2 * rng.choice([-1, 1], N)) + rng.normal(0, .02, N))
+    # aimed at the arc from the road: origin on road, direction towards a point on the arc
+    px, py = rng.uniform(200, 550, N), rng.uniform(200, 550, N)
+    tx, ty = 375 + sx * U + (84 + rng.normal(0, 1, N)) * np.cos(th), 375 + sy * U + (84 + rng.normal(0, 1, N)) * np.sin(th)
+    sets["aim_arc"] = (px, py, np.arctan2(-(ty - py), tx - px))
+    # grazing along the straight walls
+    sets["graze"] = (375 + side * (rw - rng.uniform(0, 8, N)), rng.uniform(0, 750, N), rng.choice([np.pi/2, -np.pi/2], N) + rng.normal(0, .03, N))
+    for name, (x, y, a) in sets.items():
+        t0 = time.time()
+        o = run(L, x, y, a)
+        bad = (o[:, 0] != o[:, 2]) | ((o[:, 1] != o[:, 3]))
+        # off-screen exits: old reports the break sample, new may report 63; both say "no hit"
+        offscreen_equiv = (o[:, 1] == 0) & (o[:, 3] == 0) & (o[:, 0] >= 1)
+        real_bad = bad & ~offscreen_equiv
+        tests = o[:, 4]
+        print(f"L={L} {name:12s} n={len(x)} mismatches={real_bad.sum()} (no-hit index diffs {int((bad & offscreen_equiv).sum())})  tests mean {tests.mean():.2f} p50 {np.percentile(tests,50):.0f} p90 {np.percentile(tests,90):.0f} p99 {np.percentile(tests,99):.0f} max {tests.max()}  >3: {(tests>3).mean()*100:.1f}%  {time.time()-t0:.1f}s")
+        if real_bad.any():
+            i = np.nonzero(real_bad)[0][:5]
+            for j in i: print("   ", np.float32(x[j]), np.float32(y[j]), np.float32(a[j]), o[j])
+            sys.exit(1)

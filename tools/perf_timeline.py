@@ -8,9 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from bench import N_AGENTS, ROUTES8  # noqa: E402
+from bench import CONFIGS  # noqa: E402
 from marl_traffic_intersection_b200 import BatchedIntersectionEnv  # noqa: E402
 
+N_AGENTS, ROUTES8 = CONFIGS["C5"]["agents"], CONFIGS["C5"]["routes"]
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 100
