@@ -42,7 +42,7 @@ constexpr int DYN_WARPS = ISX_DYN_WARPS;   // envs (warps) per CTA in k_traffic
 constexpr int EGO_THREADS = ISX_EGO_THREADS;
 constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
 #ifndef ISX_LID_MINB
-#define ISX_LID_MINB 8
+#define ISX_LID_MINB 5      // 39 registers instead of 32: 844 -> 788 us at 65,536 envs (6: 818, 4: 807, 3: 808); the kernel is issue-bound, not latency-bound
 #endif
 constexpr int LID_THREADS = 256;
 #ifndef ISX_TRAFFIC_PACK2
@@ -630,8 +630,10 @@ k_features(const Dev d, int mode) {
             cand[e] = k | ((uint32_t)w.ia << 8) | ((uint32_t)w.span << 16) | ((uint32_t)w.kmin << 24);
         }
     }
-    float* orow = d.obs + (size_t)ga * ISX_OBS_DIM;
-    float* crow = d.obs_c + (size_t)ga * 32;       // compact copy of the same 31 floats (+ alive flag) for the host-buffer step
+    // The 31 features (+ alive flag) of the warp's 8 egos are staged in shared memory and leave as whole-row stores: 31
+    // scattered 4-byte stores per ego and copy cost a 32-byte L2 sector each (1.4 GB of L2 traffic per launch at 65,536 envs).
+    __shared__ float s_out[FEAT_THREADS / 32][8][33];
+    float* so = s_out[threadIdx.x >> 5][lane >> 2];
     // ---- merge the four sorted partial lists: five rounds of a quad-wide lexicographic (distance, list index) minimum,
     //      plus a sixth minimum that is only looked at for the tie test below
     float fd[6]; int fk[5];
@@ -674,29 +676,45 @@ k_features(const Dev d, int mode) {
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
         const int r = it == 0 ? q : (q == 3 ? 4 : -1);
-        if (!ok || r < 0) continue;
+        if (r < 0) continue;
         const int mk = r == 0 ? fk[0] : r == 1 ? fk[1] : r == 2 ? fk[2] : r == 3 ? fk[3] : fk[4];
         float f5[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (mk != 0x7fffffff) {
+        if (ok && mk != 0x7fffffff) {
             Pose ot; int intent;
             if (mk < N) { const int j = env * N + mk; ot = Pose{d.ex[j], d.ey[j], d.ev[j], d.eh[j]}; intent = d.route_meta[mk].intent; }
             else { const int j = env * d.M + (mk - N); ot = Pose{d.nx[j], d.ny[j], d.nv[j], d.nh[j]}; intent = d.route_meta[N + d.nroute[j]].intent; }
             obs_neighbor_features(me, ot, intent, f5);
         }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { orow[6 + 5 * r + i] = f5[i]; crow[6 + 5 * r + i] = f5[i]; }
+        for (int i = 0; i < 5; ++i) so[6 + 5 * r + i] = f5[i];
     }
-    if (ok && q == 1) {                            // the six ego features (:431-458); zeros for a dead ego (:426-429)
+    if (q == 1) {                                  // the six ego features (:431-458); zeros for a dead ego (:426-429)
         float f6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (alive) {
+        if (ok && alive) {
             const F2* path = d.route_path + (size_t)self * PATH_LEN;
             obs_ego_features(me, path[min(d.epidx[ga] + 10, PATH_LEN - 1)], f6);
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { orow[i] = f6[i]; crow[i] = f6[i]; }
-        crow[31] = alive ? 1.0f : 0.0f;
+        for (int i = 0; i < 6; ++i) so[i] = f6[i];
+        so[31] = alive ? 1.0f : 0.0f;
+    }
+    __syncwarp();
+    {
+        const int ga0 = (int)((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) >> 2);   // first ego of this warp
+        const int nag = min(8, agents - ga0);                                            // <= 0: nothing in range
+        const float(*sw)[33] = s_out[threadIdx.x >> 5];
+        float* crow = d.obs_c + (size_t)ga0 * 32;  // compact record for the host-buffer step: 32 floats per ego, contiguous over egos
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            if (a < nag) {
+                const float v = sw[a][lane];
+                crow[a * 32 + lane] = v;
+                if (lane < 31) d.obs[(size_t)(ga0 + a) * ISX_OBS_DIM + lane] = v;
+            }
+        }
     }
 }
+
 
 // ------------------------------------------------------------------------------------------------ k_lidar_obs
 // Road march for the 32 rays of a warp (must be called by all 32 lanes, converged).  Every lane first jumps over the

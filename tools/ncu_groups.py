@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "marl-traffic-intersection_b200", "csrc")
+CSRC = os.environ.get("ISX_CSRC") or os.path.join(ROOT, "marl-traffic-intersection_b200", "csrc")   # ISX_CSRC: sources of the profiled build
 rep, kern = sys.argv[1], sys.argv[2]
 mangled = sys.argv[3] if len(sys.argv) > 3 else kern
 txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kern, "100000", mangled],
