@@ -383,6 +383,11 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         if (!build_road_tables(q.lanes, &rt)) { isx_destroy(h); return fail(ISX_E_STATE, "road map is not mirror-symmetric"); }
         F2* d_paths; RouteMeta* d_meta; uint32_t* d_bits; uint8_t* d_skip;
         ALLOC(d_paths, paths.size()); UPLOAD(d_paths, paths.data(), sizeof(F2) * paths.size());
+        std::vector<float> far2(paths.size());
+        for (size_t r0 = 0; r0 + PATH_LEN <= paths.size(); r0 += PATH_LEN) path_far_table(paths.data() + r0, far2.data() + r0);
+        float* d_far2;
+        ALLOC(d_far2, far2.size()); UPLOAD(d_far2, far2.data(), sizeof(float) * far2.size());
+        q.route_far2 = d_far2;
         ALLOC(d_meta, meta.size()); UPLOAD(d_meta, meta.data(), sizeof(RouteMeta) * meta.size());
         rt.bits.resize(road_bits_bytes() / 4, 0u);        // padded to 16 B multiples for the kernel's vector copy
         rt.skip.resize(road_skip_bytes(), 0);
@@ -391,7 +396,7 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         q.route_path = d_paths; q.route_meta = d_meta; q.road_bits = d_bits; q.road_skip = d_skip; q.rel_angle = d_rel;
         q.box_lo = rt.box_lo; q.box_hi = rt.box_hi; q.ana = rt.ana;
     }
-    d.route_path = gd[0].route_path; d.route_meta = gd[0].route_meta; d.road_bits = gd[0].road_bits; d.road_skip = gd[0].road_skip;
+    d.route_path = gd[0].route_path; d.route_far2 = gd[0].route_far2; d.route_meta = gd[0].route_meta; d.road_bits = gd[0].road_bits; d.road_skip = gd[0].road_skip;
     d.rel_angle = d_rel; d.box_lo = gd[0].box_lo; d.box_hi = gd[0].box_hi; d.ana = gd[0].ana;
 
     // ---- state, scratch and output buffers, shared by all groups
@@ -444,7 +449,7 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
             Dev v = shard_of(d, first, q.E, g);
             v.lanes = q.lanes; v.use_team = q.use_team; v.respawn = q.respawn; v.max_steps = q.max_steps;
             v.traffic = q.traffic; v.T = q.T; v.auto_reset = q.auto_reset; v.rc = q.rc; v.seed = q.seed; v.env_base = q.env_base;
-            v.route_path = q.route_path; v.route_meta = q.route_meta; v.road_bits = q.road_bits; v.road_skip = q.road_skip;
+            v.route_path = q.route_path; v.route_far2 = q.route_far2; v.route_meta = q.route_meta; v.road_bits = q.road_bits; v.road_skip = q.road_skip;
             v.box_lo = q.box_lo; v.box_hi = q.box_hi; v.ana = q.ana;
             grp.d = v; grp.first = first;
             first += q.E;

@@ -28,6 +28,7 @@ struct Dev {
     // ---- constant tables
     const F2* route_path;        // [(N + T)][160]   ego slot i -> i, traffic route r -> N + r
     const RouteMeta* route_meta; // [(N + T)]
+    const float* route_far2;     // [(N + T)][160]   far-window bound of Car::update_path_index (isx_sim.cuh path_far_table)
     const uint32_t* road_bits;   // [ROAD_ROWS][ROAD_WORDS]
     const uint8_t* road_skip;    // [SKIP_DIM][SKIP_DIM]
     int box_lo, box_hi;          // strip interior [box_lo, box_hi] x [0,749] (and transpose) is all road

@@ -142,6 +142,24 @@ void isxh_road_events(int lanes, int n, const float* cx, const float* cy, const 
         o[0] = k0; o[1] = h0; o[2] = k1; o[3] = h1; o[4] = tests; o[5] = ray_safe_samples(t->ana, ray);
     }
 }
+// Car::update_path_index with the near/far shortcut against the plain 50-point scan, on n (index, position) samples of one route.
+int isxh_path_index(int lanes, const char* start, const char* end, int n, const int* idx, const float* x, const float* y, int* fast, int* full) {
+    RouteHost r;
+    const int rc = build_route(lanes, start, end, &r);
+    if (rc) return rc;
+    float far2[PATH_LEN];
+    path_far_table(r.path, far2);
+    int skipped = 0;
+    for (int i = 0; i < n; ++i) {
+        fast[i] = path_index_update(r.path, far2, idx[i], x[i], y[i]);
+        full[i] = path_index_update(r.path, nullptr, idx[i], x[i], y[i]);
+        const int st = idx[i] < 0 ? 0 : idx[i];
+        const float dx = r.path[st].x - x[i], dy = r.path[st].y - y[i];
+        (void)dx; (void)dy;
+    }
+    (void)skipped;
+    return 0;
+}
 int isxh_ana_enabled(int lanes) { return tables_for(lanes)->ana.enabled; }
 int isxh_self_status(int lanes, float x, float y, float h, float gx, float gy, float px, float py) {
     return ego_self_status(lanes, x, y, h, F2{gx, gy}, F2{px, py});

@@ -30,7 +30,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #define ISX_FEAT_THREADS 128
 #endif
 #ifndef ISX_TRAFFIC_MINB
-#define ISX_TRAFFIC_MINB 32   // 32-thread CTAs: 32 per SM = 64 registers (16 words of spill): neutral at 8192 envs, where the
+#define ISX_TRAFFIC_MINB 48   // 32-thread CTAs, 42 registers (with four envs per warp: 32 -> 106.9 us, 48 -> 103.2 at 65536 envs); earlier: 64 registers neutral at 8192 envs, where the
 #endif                        // longest env chain sets the time, 145 -> 132 us at 65536 envs, where resident warps do
 #ifndef ISX_EGO_MINB
 #define ISX_EGO_MINB 8        // 64 registers, no spills (76.3 -> 75.1 us at 65536 envs; tighter caps spill and lose)
@@ -45,10 +45,10 @@ constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
 #define ISX_LID_MINB 5      // 39 registers instead of 32: 844 -> 788 us at 65,536 envs (6: 818, 4: 807, 3: 808); the kernel is issue-bound, not latency-bound
 #endif
 constexpr int LID_THREADS = 256;
-#ifndef ISX_TRAFFIC_PACK2
-#define ISX_TRAFFIC_PACK2 1
+#ifndef ISX_TRAFFIC_LANES
+#define ISX_TRAFFIC_LANES 8
 #endif
-constexpr bool TRAFFIC_PACK2 = ISX_TRAFFIC_PACK2 != 0;   // k_traffic<16>: two envs per warp when npc_capacity <= 16
+constexpr int TRAFFIC_LANES = ISX_TRAFFIC_LANES;   // lanes per env in k_traffic: 8 (four envs per warp), 16 or 32
 #ifndef ISX_WARP_GRAB
 #define ISX_WARP_GRAB 2
 #endif
@@ -108,7 +108,11 @@ struct Grp {
         for (int o = L / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o, L));
         return v;
     }
-    __device__ __forceinline__ int umax(int v) const { return L == 32 ? v : max(v, __shfl_xor_sync(FULL, v, 16)); }   // warp-uniform bound
+    __device__ __forceinline__ int umax(int v) const {                                                                // warp-uniform bound
+        if (L <= 16) v = max(v, __shfl_xor_sync(FULL, v, 16));
+        if (L <= 8) v = max(v, __shfl_xor_sync(FULL, v, 8));
+        return v;
+    }
 };
 
 // Car::update_path_index with the 50-point window spread over the L lanes of a group; first minimum wins (Car.cpp:62-70).
@@ -137,21 +141,14 @@ __device__ __forceinline__ int group_path_index(const F2* __restrict__ path, int
     return bi;
 }
 
+// One env's traffic update on a group of L lanes (wl = lane within the warp; all 32 lanes of the warp call this together,
+// each group with its own env).  env_raw >= d.E: an idle group (c = 0, no writes).
 template <int L>
-__global__ void __launch_bounds__(DYN_WARPS * 32, ISX_TRAFFIC_MINB)
-k_traffic(const Dev d, float dt, float spawn_prob) {
-    pdl_launch_dependents();
-    pdl_wait();
-    constexpr int EPW = 32 / L;                                       // envs per warp
-    __shared__ NpcSmem sm_all[DYN_WARPS * EPW];
-    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+__device__ __forceinline__ void traffic_env(const Dev& d, float dt, float spawn_prob, int env_raw, int wl, NpcSmem& sm) {
     const int sub = wl / L, lane = wl % L;                            // `lane`: my lane within the env's group
     const Grp<L> g{sub * L};
-    const int env_raw = (blockIdx.x * DYN_WARPS + warp) * EPW + sub;
-    if (env_raw - sub >= d.E) return;                                 // whole warp leaves; only warp-level sync below
-    const bool env_ok = env_raw < d.E;                                // an odd env count leaves the last half idle (c = 0, no writes)
+    const bool env_ok = env_raw < d.E;                                // idle groups: c = 0, no writes
     const int env = env_ok ? env_raw : d.E - 1;
-    NpcSmem& sm = sm_all[warp * EPW + sub];
     const int N = d.N;
     const uint32_t genv = (uint32_t)(d.env_base + env);
     int c = env_ok ? d.ncount[env] : 0;
@@ -221,8 +218,18 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     if (lane < c) {
         cur = Pose{sm.x[lane], sm.y[lane], sm.v[lane], sm.h[lane]};
         my_route = sm.route[lane];
+        my_pidx = sm.pidx[lane];
+    }
+    // first path-index update of every NPC (Car.cpp:47-74), the 50-point window spread over the lanes of the group: a lane
+    // scanning its own NPC's window alone kept 2.4 of 32 lanes busy for a quarter of the kernel's instructions
+    const int cmax = g.umax(c);
+    for (int i = 0; i < cmax; ++i) {
+        const F2* path_i = d.route_path + (size_t)(N + g.shfl(my_route, i)) * PATH_LEN;
+        const int pi = group_path_index<L>(path_i, g.shfl(my_pidx, i), g.shfl(cur.x, i), g.shfl(cur.y, i), lane);
+        if (lane == i) my_pidx = pi;
+    }
+    if (lane < c) {
         const F2* path = d.route_path + (size_t)(N + my_route) * PATH_LEN;
-        my_pidx = path_index_update(path, sm.pidx[lane], cur.x, cur.y);
         const float steer_cmd = npc_steer_cmd(cur, path[min(my_pidx + 12, PATH_LEN - 1)]);
         my_steer = car_steer_update(sm.steer[lane], steer_cmd);
         // inlined on purpose: heading sin/cos and the centre distance do not depend on the steering chain
@@ -232,7 +239,6 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
         my_tan = tanf_nc(my_steer);
     }
     ISX_STAMP(2);
-    const int cmax = g.umax(c);
     for (int i = 0; i < cmax; ++i) {
         const bool on = i < c;                                     // my group still has an NPC i
         Pose me;
@@ -335,15 +341,43 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     if (env_ok && lane == 0) { d.ncount[env] = c; d.next_uid[env] = next_uid; d.events[env] = evt; }
     ISX_STAMP(5);
     if (d.trace && env_ok && lane == 0) d.trace[(size_t)env * 16 + 6] = c;
-    if (env_ok) {
+    if (env_ok && lane == 0) {
         uint32_t* st = d.env_stats + (size_t)env * STAT_SLOTS;
-        uint32_t inc = 0;
-        if (lane == ST_SPAWNED) inc = (uint32_t)evt.spawned;
-        else if (lane == ST_REMOVED) inc = (uint32_t)__popc(evt.removed_mask);
-        else if (lane == ST_COLLIDED) inc = (uint32_t)__popc(evt.collided_mask);
-        else if (lane == ST_OVERFLOW) inc = overflow;
-        if (inc) st[lane] += inc;
+        if (evt.spawned) st[ST_SPAWNED] += 1u;
+        if (evt.removed_mask) st[ST_REMOVED] += (uint32_t)__popc(evt.removed_mask);
+        if (evt.collided_mask) st[ST_COLLIDED] += (uint32_t)__popc(evt.collided_mask);
+        if (overflow) st[ST_OVERFLOW] += overflow;
     }
+}
+
+// L lanes per env.  L = 8 (the default): FOUR envs share a warp — the mean env holds about one NPC, so the list-order chain
+// of an env runs on one or two lanes whatever the group width, and packing more envs into one instruction stream divides the
+// warps this latency-bound kernel has to retire (2 envs per warp: 102 -> 77 us at 32768 envs; 4 per warp: see DESIGN.md).  A group
+// of 8 lanes holds at most 8 NPCs: when an env of the warp already has 8 and room for a ninth (capacity > 8), the warp
+// steps its four envs one after the other on all 32 lanes instead (rare: the largest population observed is 13).
+template <int L>
+__global__ void __launch_bounds__(DYN_WARPS * 32, ISX_TRAFFIC_MINB)
+k_traffic(const Dev d, float dt, float spawn_prob) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int EPW = 32 / L;                                       // envs per warp
+    __shared__ NpcSmem sm_all[DYN_WARPS * EPW];
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const int env0 = (blockIdx.x * DYN_WARPS + warp) * EPW;           // first env of this warp
+    if (env0 >= d.E) return;                                          // whole warp leaves; only warp-level sync below
+    if (L < 32) {
+        const int e = env0 + wl / L;
+        bool wide = false;
+        if (e < d.E && d.M > L) {
+            const bool reset_now = d.auto_reset && (d.terminated[e] | d.truncated[e]);
+            wide = !reset_now && d.ncount[e] >= L;
+        }
+        if (__any_sync(FULL, wide)) {
+            for (int k = 0; k < EPW; ++k) { traffic_env<32>(d, dt, spawn_prob, env0 + k, wl, sm_all[warp * EPW]); __syncwarp(); }
+            return;
+        }
+    }
+    traffic_env<L>(d, dt, spawn_prob, env0 + wl / L, wl, sm_all[warp * EPW + wl / L]);
 }
 
 // ------------------------------------------------------------------------------------------------ k_ego
@@ -409,12 +443,51 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
             if (actions) { thr = actions[2 * ai]; st = actions[2 * ai + 1]; }
             else philox_action(d.seed, genv, tick, (uint32_t)a, thr, st);
             car_update(p, steer, acc, thr, st, dt);
-            pidx = path_index_update(d.route_path + (size_t)a * PATH_LEN, pidx, p.x, p.y);
             const RouteMeta m = d.route_meta[a];
             rew = reward_base(d.rc, p.x, p.y, p.v, acc, steer, m.goal, d.max_progress, pd, pa0, pa1);
             status = ego_self_status(d.lanes, p.x, p.y, p.h, m.goal, m.goal_prev);     // :166-290
             done = status != ISX_ALIVE;
         } else { status = ISX_DEAD; done = true; }
+    }
+    // -- Car::update_path_index (Car.cpp:47-74; :163 of the step; nothing above reads the new index).  Every lane scans the
+    //    first PATH_NEAR points of its window; the far part is only needed when the bound of path_index_update fails (a car
+    //    far off its path) and is then scanned by the whole warp for that one lane — one straggler no longer makes 32 lanes
+    //    walk 34 more points each.
+    {
+        const bool upd = is_ego && !frozen && alive;
+        const int start = pidx < 0 ? 0 : pidx;
+        float best = INFINITY, d0 = 0.0f;
+        int bi = start;
+        if (upd) path_index_near(d.route_path + (size_t)a * PATH_LEN, start, p.x, p.y, best, bi, d0);
+        const bool need = upd && !(2.0f * (d0 + best) < d.route_far2[(size_t)a * PATH_LEN + min(start, PATH_LEN - 1)]);
+        unsigned todo = __ballot_sync(FULL, need);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int s0 = __shfl_sync(FULL, start, src) + PATH_NEAR, s1 = min(s0 - PATH_NEAR + PATH_WINDOW, PATH_LEN);
+            const float sx = __shfl_sync(FULL, p.x, src), sy = __shfl_sync(FULL, p.y, src);
+            const F2* path = d.route_path + (size_t)__shfl_sync(FULL, a, src) * PATH_LEN;
+            float bd = INFINITY;
+            int bidx = 0x7fffffff;
+#pragma unroll
+            for (int r = 0; r < (PATH_WINDOW - PATH_NEAR + 31) / 32; ++r) {
+                const int i = s0 + lane + 32 * r;
+                if (i < s1) {
+                    const F2 q = path[i];
+                    const float dx = q.x - sx, dy = q.y - sy;
+                    const float dd = dx * dx + dy * dy;
+                    if (dd < bd) { bd = dd; bidx = i; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(FULL, bd, o);
+                const int oi = __shfl_xor_sync(FULL, bidx, o);
+                if (ob < bd || (ob == bd && oi < bidx)) { bd = ob; bidx = oi; }
+            }
+            if (lane == src && bd < best) { best = bd; bi = bidx; }
+        }
+        if (upd) pidx = bi;
     }
     // -- car-car override (:293-318)
     unsigned cmask = 0;                            // bit j: ego a collides with ego j > a (sub-warp numbering)
@@ -1074,7 +1147,11 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 
 cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_t st) {
     if (!d.traffic) return cudaSuccess;
-    if (d.M <= 16 && TRAFFIC_PACK2) {                // two envs per warp (the default capacity)
+    if (TRAFFIC_LANES == 8) {                         // four envs per warp (wide fallback inside the kernel)
+        const int blocks = (d.E + 4 * DYN_WARPS - 1) / (4 * DYN_WARPS);
+        return launch_pdl(k_traffic<8>, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
+    }
+    if (TRAFFIC_LANES == 16) {                        // two envs per warp
         const int blocks = (d.E + 2 * DYN_WARPS - 1) / (2 * DYN_WARPS);
         return launch_pdl(k_traffic<16>, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
     }

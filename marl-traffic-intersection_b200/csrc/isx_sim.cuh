@@ -161,14 +161,31 @@ ISX_HD_NOINL bool cars_collide(float x1, float y1, float h1, float x2, float y2,
 }
 
 // Car::update_path_index (Car.cpp:47-74): first minimum of squared distance over path[idx, min(idx+50,160)).
-// Written as 50 fixed iterations over a clamped index so that the loads are independent of the running minimum and
+// Written as fixed iterations over a clamped index so that the loads are independent of the running minimum and
 // can be issued in batches (the window tail repeats point 159, which can never win a strict `<` against itself).
-ISX_HD int path_index_update(const F2* path, int idx, float x, float y) {
+// Exactness-preserving shortcut: the window is scanned in two parts, the first PATH_NEAR points and the rest.  far2[start]
+// (path_far_table below, built on the host) is (r - 0.01)^2 with r the smallest distance from path[start] to any point of
+// the far part; a far point P_j is at least r - |car - path[start]| away from the car, so when
+// 2 (d_start + best_near) < far2[start]  —  which implies  r - 0.01 > sqrt(d_start) + sqrt(best_near)  —  every far point
+// is farther than the near minimum by more than 0.01 px (rounding of the squared distances is ~1e-7 relative) and cannot
+// win the strict `<`: the far part is skipped.  far2 == nullptr scans everything.
+constexpr int PATH_WINDOW = 50, PATH_NEAR = 16;
+ISX_HD int path_index_update(const F2* path, const float* far2, int idx, float x, float y) {
     const int start = idx < 0 ? 0 : idx;
-    float best = INFINITY;
+    float best = INFINITY, d0 = 0.0f;
     int bi = start;
-#pragma unroll 10
-    for (int j = 0; j < 50; ++j) {
+#pragma unroll
+    for (int j = 0; j < PATH_NEAR; ++j) {
+        const int i = (start + j < PATH_LEN) ? start + j : PATH_LEN - 1;
+        const F2 p = path[i];
+        const float dx = p.x - x, dy = p.y - y;
+        const float d = dx * dx + dy * dy;
+        if (j == 0) d0 = d;
+        if (d < best) { best = d; bi = i; }
+    }
+    if (far2 && 2.0f * (d0 + best) < far2[start < PATH_LEN ? start : PATH_LEN - 1]) return bi;
+#pragma unroll 17
+    for (int j = PATH_NEAR; j < PATH_WINDOW; ++j) {
         const int i = (start + j < PATH_LEN) ? start + j : PATH_LEN - 1;
         const F2 p = path[i];
         const float dx = p.x - x, dy = p.y - y;
@@ -176,6 +193,31 @@ ISX_HD int path_index_update(const F2* path, int idx, float x, float y) {
         if (d < best) { best = d; bi = i; }
     }
     return bi;
+}
+// The near part alone (the kernels finish the far part warp-cooperatively for the few lanes that need it).
+ISX_HD void path_index_near(const F2* path, int start, float x, float y, float& best, int& bi, float& d0) {
+    best = INFINITY; bi = start; d0 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < PATH_NEAR; ++j) {
+        const int i = (start + j < PATH_LEN) ? start + j : PATH_LEN - 1;
+        const F2 p = path[i];
+        const float dx = p.x - x, dy = p.y - y;
+        const float d = dx * dx + dy * dy;
+        if (j == 0) d0 = d;
+        if (d < best) { best = d; bi = i; }
+    }
+}
+// far2[i] of one 160-point path (host side; double arithmetic, rounded down)
+inline void path_far_table(const F2* path, float* far2) {
+    for (int i = 0; i < PATH_LEN; ++i) {
+        double r = INFINITY;
+        for (int j = i + PATH_NEAR; j < i + PATH_WINDOW && j < PATH_LEN; ++j) {
+            const double dx = (double)path[j].x - path[i].x, dy = (double)path[j].y - path[i].y;
+            r = fmin(r, sqrt(dx * dx + dy * dy));
+        }
+        const double m = r - 0.01;
+        far2[i] = (r == INFINITY) ? INFINITY : (m > 0.0 ? (float)(m * m * (1.0 - 1e-6)) : 0.0f);
+    }
 }
 
 // ---------------------------------------------------------------- ego status (IntersectionEnv.cpp:166-290)

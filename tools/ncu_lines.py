@@ -16,7 +16,7 @@ import tempfile
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "marl-traffic-intersection_b200", "csrc", "libisx_b200.so")
+LIB = os.environ.get("ISX_LIB") or os.path.join(ROOT, "marl-traffic-intersection_b200", "csrc", "libisx_b200.so")   # ISX_LIB: the profiled build
 
 
 def sass_lines_with_src(kernel_substr):
