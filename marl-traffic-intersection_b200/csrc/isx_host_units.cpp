@@ -149,15 +149,10 @@ int isxh_path_index(int lanes, const char* start, const char* end, int n, const 
     if (rc) return rc;
     float far2[PATH_LEN];
     path_far_table(r.path, far2);
-    int skipped = 0;
     for (int i = 0; i < n; ++i) {
         fast[i] = path_index_update(r.path, far2, idx[i], x[i], y[i]);
         full[i] = path_index_update(r.path, nullptr, idx[i], x[i], y[i]);
-        const int st = idx[i] < 0 ? 0 : idx[i];
-        const float dx = r.path[st].x - x[i], dy = r.path[st].y - y[i];
-        (void)dx; (void)dy;
     }
-    (void)skipped;
     return 0;
 }
 int isxh_ana_enabled(int lanes) { return tables_for(lanes)->ana.enabled; }

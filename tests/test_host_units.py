@@ -183,3 +183,71 @@ def test_host_obs_row_expander_matches_the_device_formula():
                 assert lib.isx_expand_obs_rows(rec.ctypes.data, hits.ctypes.data, R, dst.ctypes.data, n) == 0
                 assert (dst.view(np.uint32) == want.reshape(-1).view(np.uint32)).all(), (R, n, off)
                 assert np.isnan(buf[:off]).all() and np.isnan(buf[off + n * 127:]).all()
+
+
+def _road_events(lanes, cx, cy, ang):
+    import ctypes as C
+    lib = C.CDLL(HU)
+    n = len(cx)
+    out = np.zeros((n, 6), np.int32)
+    f = [np.ascontiguousarray(a, np.float32) for a in (cx, cy, ang)]
+    lib.isxh_road_events(lanes, n, *[a.ctypes.data_as(C.c_void_p) for a in f], out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 3, 4])
+def test_analytic_road_bound_keeps_the_march_exact(lanes):
+    """k_lidar_obs jumps over the samples ray_safe_samples proves free of road events (rounded-quadrant entry time) and
+    tests the following samples exactly.  Same first event as the skip-table march (itself pinned to Lidar.cpp's
+    sample-by-sample loop above) on uniform, axis-aligned, wall-hugging, arc-tangent and grazing rays; a no-hit ray may
+    report a later break index (cars are only tested against on-screen pixels), never a different hit."""
+    import ctypes as C
+    assert C.CDLL(HU).isxh_ana_enabled(lanes) == 1
+    rng = np.random.default_rng(100 + lanes)
+    n = 150_000
+    rw, U = 42 * lanes, 42 * lanes + 84
+    side = rng.choice([-1, 1], n)
+    eps = rng.choice([0, .01, -.01, .5, -.5, 1, -1, 1.4, -1.4, 1.6, -1.6, 3, -3], n)
+    th = rng.uniform(0, 2 * np.pi, n)
+    sx, sy = rng.choice([-1, 1], n), rng.choice([-1, 1], n)
+    rr = 84 + eps + rng.uniform(-.2, .2, n)
+    ox, oy = 375 + sx * U + rr * np.cos(th), 375 + sy * U + rr * np.sin(th)
+    px, py = rng.uniform(200, 550, n), rng.uniform(200, 550, n)
+    tx, ty = 375 + sx * U + (84 + rng.normal(0, 1, n)) * np.cos(th), 375 + sy * U + (84 + rng.normal(0, 1, n)) * np.sin(th)
+    ax = rng.choice([0, np.pi / 2, np.pi, -np.pi / 2, -np.pi, 2 * np.pi], n) + rng.choice([0, 1e-7, -1e-7, 1e-4, -1e-4, 1e-2, -1e-2], n)
+    sets = {
+        "uniform": (rng.uniform(-30, 780, n), rng.uniform(-30, 780, n), rng.uniform(-7, 7, n)),
+        "axis": (rng.integers(0, 750, n) + rng.choice([0, .5, .999, .001], n), rng.integers(0, 750, n) + rng.choice([0, .5, .999, .001], n), ax),
+        "wall": (375 + side * (rw + eps), rng.uniform(0, 750, n), rng.uniform(-np.pi, np.pi, n)),
+        "arc": (ox, oy, rng.uniform(-np.pi, np.pi, n)),
+        "arc_tangent": (ox, oy, -(th + np.pi / 2 * rng.choice([-1, 1], n)) + rng.normal(0, .02, n)),
+        "aim_arc": (px, py, np.arctan2(-(ty - py), tx - px)),
+        "graze": (rng.uniform(0, 750, n), 375 + side * (rw - rng.uniform(0, 8, n)), rng.choice([0, np.pi], n) + rng.normal(0, .03, n)),
+    }
+    for name, (x, y, a) in sets.items():
+        o = _road_events(lanes, x, y, a)
+        same_hit = (o[:, 1] == o[:, 3]) & ((o[:, 0] == o[:, 2]) | (o[:, 1] == 0))
+        assert same_hit.all(), (name, lanes, np.nonzero(~same_hit)[0][:3])
+        assert (o[:, 5] <= np.maximum(o[:, 0] - 1, 0))[o[:, 1] == 1].all(), name      # the jump never passes a hit
+
+
+def test_path_index_near_far_window_is_exact():
+    """Car::update_path_index with the far part of the 50-point window skipped under the triangle-inequality bound
+    (path_far_table) == the plain scan, for cars on, near and far from their route."""
+    import ctypes as C
+    lib = C.CDLL(HU)
+    rng = np.random.default_rng(7)
+    for lanes in (2, 3):
+        for a, b in po.default_routes(lanes):
+            r = host().route(lanes, a, b)
+            if r[1] is None:
+                continue
+            path, n = r[1], 40_000
+            idx = rng.integers(-1, 160, n).astype(np.int32)
+            base = path[np.clip(idx, 0, 159)]
+            scale = rng.choice([0.5, 5, 20, 60, 200, 600], n)
+            x = (base[:, 0] + rng.normal(0, 1, n) * scale).astype(np.float32)
+            y = (base[:, 1] + rng.normal(0, 1, n) * scale).astype(np.float32)
+            fast, full = np.zeros(n, np.int32), np.zeros(n, np.int32)
+            rc = lib.isxh_path_index(lanes, a.encode(), b.encode(), n, *[v.ctypes.data_as(C.c_void_p) for v in (idx, x, y, fast, full)])
+            assert rc == 0 and (fast == full).all(), (lanes, a, b)

@@ -1,3 +1,4 @@
+"""Ego poses of 24 C5 envs along their episodes (CPU oracle rollout with the Philox action stream) -> gpurun_out/poses.npy"""
 import sys, numpy as np
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle")
 import pyoracle as po
@@ -14,6 +15,5 @@ for e in range(24):
             if c["alive"]:
                 poses.append((c["x"], c["y"], c["heading"]))
                 others.append(cars)
-np.save("/tmp/poses.npy", np.array(poses, np.float32))
-import pickle; pickle.dump(others, open("/tmp/others.pkl", "wb"))
+np.save("gpurun_out/poses.npy", np.array(poses, np.float32))
 print(len(poses))

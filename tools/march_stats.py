@@ -1,6 +1,8 @@
+"""How many exact sample tests a beam needs after the analytic jump, on ego poses of a C5 rollout (tools/march_poses.py writes
+gpurun_out/poses.npy): python tools/march_poses.py && python tools/march_stats.py"""
 import ctypes as C, numpy as np, sys
 lib = C.CDLL("/root/repo/marl-traffic-intersection_b200/csrc/libisx_host_units.so")
-P = np.load("/tmp/poses.npy")
+P = np.load("gpurun_out/poses.npy")
 R = 72
 deg = -180.0 + np.arange(R, dtype=np.float32) * np.float32(360.0 / (R - 1))
 rel = (deg.astype(np.float32) * np.float32(np.pi) / np.float32(180.0)).astype(np.float32)

@@ -1,3 +1,5 @@
+"""Ray-level validation of the analytic road bound (isx_sim.cuh ray_safe_samples + exact samples) against the skip-table march on
+millions of uniform and adversarial rays, all lane counts (CPU, host build):  python tools/march_validate.py [seed] [rays per set]"""
 import ctypes as C, numpy as np, sys, time
 lib = C.CDLL("/root/repo/marl-traffic-intersection_b200/csrc/libisx_host_units.so")
 def run(L, cx, cy, ang):
