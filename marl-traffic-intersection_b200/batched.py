@@ -254,7 +254,8 @@ class BatchedIntersectionEnv:
         a, b, t, r = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
         _lib.check(self._lib, self._lib.isx_host_step_info(self._h, C.byref(a), C.byref(b), C.byref(t), C.byref(r)))
         return {"h2d": a.value, "d2h": b.value, "host_expand_threads": t.value, "pipeline_ranges": r.value,
-                "obs_transport": "compact: 32 f32 + lidar_rays u8 per agent over PCIe, 127-float rows rebuilt bit-identically by host threads"}
+                "obs_transport": ("compact: 32 f32 + lidar_rays u8 per agent over PCIe, 127-float rows rebuilt bit-identically by host threads"
+                                  if t.value > 0 else "rows: the 127-float rows themselves cross PCIe into the pinned view (small batch)")}
 
     def rollout(self, steps: int, dt: float = 1.0 / 60.0):
         """`steps` steps with on-device Philox actions (random-action rollout of BASELINE.json)."""

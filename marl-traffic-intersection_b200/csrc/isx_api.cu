@@ -504,7 +504,8 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         // every group is one range.
         if (n_groups == 1) {
             // 65,536 envs (compact transport, 12 host threads): 1,2,3,4,6 -> 3.33 ms; 4 equal 3.59; 8 equal 3.57; 1,2,2,3 3.44
-            int w[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, nw = d.E >= 32768 ? 5 : d.E >= 1024 ? 4 : 1;
+            // below 16,384 agents every kernel sits at its latency floor (one wave): cutting the batch only repeats that floor per range
+            int w[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, nw = d.E >= 32768 ? 5 : (d.E >= 1024 && EN >= 16384) ? 4 : 1;
             if (d.E >= 32768) { w[0] = 1; w[1] = 2; w[2] = 3; w[3] = 4; w[4] = 6; }   // a small first range starts the copy engine early
             if (const char* plan = getenv("ISX_PIPE_PLAN")) {
                 int k = 0;
@@ -538,7 +539,7 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         T = T >= 4 ? (T * 3) / 4 : T;      // leave cores to the caller's thread and the driver (16 CPUs: 12 -> 3.42 ms, 14 -> 3.76, 8 -> 3.69)
         if (T > 32) T = 32;
         if (const char* ht = getenv("ISX_HOST_THREADS")) { const int v = atoi(ht); if (v >= 0 && v <= 256) T = v; }
-        if (EN < 4096) T = 0;
+        if (EN < 16384) T = 0;             // small batches ship the rows themselves (enqueue_pinned_step): no thread wake-ups
         // copy chunks: every pipeline piece is drained in `sub` chunks so that the host threads start on a piece while its
         // tail is still crossing PCIe (ISX_PIPE_CHUNKS overrides; about 1M compact-record bytes per chunk at the least)
         {
@@ -745,6 +746,12 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::ve
         for (; next_chunk < h->chunks.size() && h->chunks[next_chunk].piece == (int)c; ++next_chunk) {
             const isx_handle::Chunk& ch = h->chunks[next_chunk];
             const size_t n = ch.a1 - ch.a0;
+            if (!h->pool) {
+                // small batches (no host threads): the rows themselves cross PCIe, straight into the pinned obs view — a few
+                // MB take less time on the copy engine than one host thread needs to rebuild them (C2: 266 -> see DESIGN.md)
+                CK(cudaMemcpyAsync(h->h_obs + ch.a0 * ISX_OBS_DIM, d.obs + ch.a0 * ISX_OBS_DIM, sizeof(float) * n * ISX_OBS_DIM, cudaMemcpyDeviceToHost, h->copy_stream));
+                continue;
+            }
             CK(cudaMemcpyAsync(h->h_rec + ch.a0 * 32, d.obs_c + ch.a0 * 32, sizeof(float) * n * 32, cudaMemcpyDeviceToHost, h->copy_stream));
             CK(cudaMemcpyAsync(h->h_hitc + ch.a0 * (size_t)d.R, d.hit_c + ch.a0 * (size_t)d.R, n * (size_t)d.R, cudaMemcpyDeviceToHost, h->copy_stream));
             CK(cudaMemcpyAsync(h->h_seq + 1 + next_chunk, h->d_seq, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->copy_stream));
@@ -800,8 +807,8 @@ static int host_step_into(isx_handle* h, float dt, cudaStream_t st, float* dst, 
     if (h->pool) {
         if (rc) h->pool->release_all();
         h->pool->wait_step();                                    // every row of `dst` is complete (and fenced) after this
-    } else if (!rc) {
-        expand_obs_rows(h->h_rec, h->h_hitc, h->d.R, dst, (size_t)h->d.E * h->d.N);
+    } else if (!rc && dst != h->h_obs) {
+        std::memcpy(dst, h->h_obs, sizeof(float) * (size_t)h->d.E * h->d.N * ISX_OBS_DIM);   // the copy engine filled the pinned view
     }
     return rc;
 }
@@ -853,7 +860,7 @@ int isx_host_step_info(isx_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes, in
     if (!h) return fail(ISX_E_ARG, "null handle");
     const int64_t EN = (int64_t)h->d.E * h->d.N;
     if (h2d_bytes) *h2d_bytes = EN * 2 * (int64_t)sizeof(float);
-    if (d2h_bytes) *d2h_bytes = EN * (32 * (int64_t)sizeof(float) + h->d.R) + (int64_t)h->small_bytes;
+    if (d2h_bytes) *d2h_bytes = (h->pool ? EN * (32 * (int64_t)sizeof(float) + h->d.R) : EN * (int64_t)sizeof(float) * ISX_OBS_DIM) + (int64_t)h->small_bytes;
     if (host_threads) *host_threads = h->host_threads;
     if (ranges) *ranges = (int32_t)h->pipe.size();
     return ISX_OK;

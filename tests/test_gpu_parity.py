@@ -137,18 +137,21 @@ def test_state_injection_roundtrip_and_resync():
     b.close()
 
 
-def test_pipelined_host_step_equals_device_step():
-    """isx_step_pinned cuts the env range into 4 shards and overlaps their device->host copies with the next shard's
+@pytest.mark.parametrize("E", [1024, 6144])
+def test_pipelined_host_step_equals_device_step(E):
+    """Both transports of the host-buffer step: 1024 envs x 3 egos ship the obs rows themselves (small batch, no host
+    threads), 6144 x 3 ship compact records that the library's host threads expand.  isx_step_pinned cuts the env range into 4 shards and overlaps their device->host copies with the next shard's
     kernels, replaying the whole step from a CUDA graph captured per dt; results must be identical to the single-launch
     device step (and therefore to the checker), also when dt changes between calls (graph re-captured) and when device
     steps are interleaved on the caller's stream."""
     import torch
-    cfg = dict(num_envs=1024, num_agents=3, num_lanes=3, ego_routes=[("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")],
+    cfg = dict(num_envs=E, num_agents=3, num_lanes=3, ego_routes=[("IN_6", "OUT_2"), ("IN_4", "OUT_8"), ("IN_5", "OUT_7")],
                use_team_reward=True, traffic_flow=True, traffic_density=2.0, seed=21)
     a_env, b_env = _benv()(cfg), _benv()(cfg)
+    assert (b_env.host_step_bytes()["host_expand_threads"] > 0) == (E * 3 >= 16384)
     rng = np.random.default_rng(0)
     for t in range(60):
-        act = rng.uniform(-1, 1, (1024, 3, 2)).astype(np.float32)
+        act = rng.uniform(-1, 1, (E, 3, 2)).astype(np.float32)
         dt = (1.0 / 60.0, 1.0 / 60.0, 1.0 / 30.0, 0.02)[(t // 5) % 4]
         obs_d, rew_d, term_d, trunc_d, info = a_env.step(torch.from_numpy(act).cuda(), dt)
         if t % 7 == 3:                     # a device-buffer step in between: the replay must stay ordered behind it
