@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import pyoracle as po
-from parity_util import checker_class, free_run, make_pair, pursuit_policy
+from parity_util import checker_class, compare_step, free_run, make_pair, pursuit_policy
 
 pytestmark = pytest.mark.gpu
 
@@ -313,6 +313,35 @@ def test_npc_capacity_overflow_is_counted_not_fatal():
     b.rollout(400)
     st = b.stats()
     assert st["npc_overflow"] > 0 and int(b.buf["npc_count"].max()) <= 3 and st["agent_steps"] == 64 * 400
+    b.close()
+
+
+def test_full_eight_lane_group_matches_until_the_first_dropped_spawn():
+    """k_traffic gives an env 8 lanes (four envs per warp).  With npc_capacity = 8 there is no wide fallback: a group whose
+    8 lanes all hold an NPC must still match the reference bit for bit, up to the step at which the bounded list drops a
+    spawn the reference's unbounded list would take (counted in npc_overflow; from there the two legitimately differ)."""
+    import torch
+    cfg = dict(num_envs=8, num_agents=1, num_lanes=3, ego_routes=[("IN_6", "OUT_2")], traffic_flow=True, traffic_density=30.0,
+               npc_capacity=8)
+    b, refs = make_pair(_benv(), cfg, seed=11)
+    b.reset()
+    for r in refs:
+        r.reset()
+    full, t = False, 0
+    for t in range(1, 1500):
+        act = np.stack([po.philox_actions(11, e, refs[e].tick + 1, 1) for e in range(8)])
+        b.step(torch.from_numpy(act).cuda())
+        if b.stats()["npc_overflow"] > 0:
+            break
+        outs = [refs[e].step(act[e]) for e in range(8)]
+        buf = compare_step(b, refs, outs, f"step {t}")
+        full = full or bool((buf["npc_count"] == 8).any())
+        need = np.array([o["terminated"] or o["truncated"] for o in outs])
+        if need.any():
+            b.reset(torch.from_numpy(need.astype(np.uint8)).cuda())
+            for e in np.nonzero(need)[0]:
+                refs[e].reset()
+    assert full and t > 30, (full, t)
     b.close()
 
 
