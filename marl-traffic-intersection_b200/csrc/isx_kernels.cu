@@ -1,14 +1,14 @@
 // isx_kernels.cu — the step kernels (sm_100a).
 //
-//   k_traffic   : one WARP per env.  NPC traffic flow (spawn draw, Gauss-Seidel planner/integrator in list order,
+//   k_traffic   : 8 lanes per env, four envs per warp.  NPC traffic flow (spawn draw, Gauss-Seidel planner/integrator in list order,
 //                 NPC-NPC SAT, ordered erase), lanes spread over ghost-path points / other NPCs / path-window
 //                 points.  Replaces TrafficFlow.cpp:317-367.  Only launched with traffic flow on.
 //   k_ego       : one LANE per ego, an env = a sub-warp of 2^ceil(log2 N) lanes: physics, reward, status, car-car
 //                 override, bonuses, team mix, respawn, termination.  Replaces IntersectionEnv.cpp:137-370.
-//   k_features  : one THREAD per ego: the 31 ego/neighbour observation features + the per-ego list of cars its
+//   k_features  : FOUR lanes per ego: the 31 ego/neighbour observation features + the per-ego list of cars its
 //                 beams can touch (with angular beam windows).  Replaces IntersectionEnv.cpp:418-508.
-//   k_lidar_obs : one THREAD per (ego, beam), persistent CTAs with the folded road bitmap + skip table in shared
-//                 memory, warps claim 32-beam pieces dynamically: accelerated exact road march + slab/verify
+//   k_lidar_obs : one THREAD per (ego, beam), persistent CTAs with the folded road bitmap in shared
+//                 memory, warps claim 32-beam pieces dynamically: analytic road bound + exact sample tests, slab/verify
 //                 against the other cars' pixel rectangles.  Writes the lidar part of the obs rows coalesced.
 //                 Replaces Lidar.cpp:16-90 and IntersectionEnv.cpp:374-390, 510-514.
 //
@@ -81,7 +81,7 @@ struct NpcSmem {
 // Programmatic dependent launch (sm_90+): the four step kernels are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of kernel k+1 may become resident while kernel k drains
 // its last wave.  Every kernel first lets ITS successor start (launch_dependents), runs whatever does not depend on the
-// predecessor (k_lidar_obs: staging 27 KB of constant tables per CTA), and only then waits for the predecessor grid to
+// predecessor (k_lidar_obs: staging 18 KB of constant tables per CTA), and only then waits for the predecessor grid to
 // complete and flush (wait) — nothing a predecessor writes is touched before that.  Both are no-ops in a plain launch.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -91,11 +91,11 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // in list order, NPC-NPC SAT, ordered erase.  The lanes spread over path-window points / other NPCs / ghost-path points.
 // Reads the egos' PRE-step positions (spawn blocking, :244-249), so it runs before k_ego.  Only launched when traffic
 // flow is enabled.
-// L = lanes per env.  L = 32: one env per warp, any NPC capacity.  L = 16 (npc_capacity <= 16, the default): TWO envs
-// share a warp, one per half — the mean env has ~1 NPC, so a whole warp per env runs its list-order chain on one or two
-// lanes; packing two envs into the same instruction stream halves the warps the latency-bound kernel has to retire.
-// Every warp-wide primitive below is group-wide: shuffles of width L, ballots masked to the group's half, loop bounds
-// made warp-uniform (max over the halves) with the body predicated per half.
+// L = lanes per env.  L = 32: one env per warp, any NPC count.  L = 8 (the default) / 16: FOUR / two envs share a warp,
+// one per group of L lanes — the mean env has ~1 NPC, so a whole warp per env runs its list-order chain on one or two
+// lanes; packing more envs into the same instruction stream divides the warps the latency-bound kernel has to retire.
+// Every warp-wide primitive below is group-wide: shuffles of width L, ballots masked to the group's lanes, loop bounds
+// made warp-uniform (max over the groups) with the body predicated per group.
 template <int L>
 struct Grp {
     static constexpr unsigned MASK = L == 32 ? FULL : ((1u << (L & 31)) - 1u);
@@ -833,8 +833,8 @@ __device__ __forceinline__ int warp_road_event(bool active, const uint32_t* bits
 }
 
 // One THREAD per (ego, beam), beams of all egos laid end to end; persistent CTAs walk 256-beam chunks, so the only
-// block-level synchronisation is the one after the road tables are staged in shared memory (28 KB per CTA: folded
-// bitmap + skip table + beam angles).  Everything per ego comes from k_features through L1/L2.
+// block-level synchronisation is the one after the road tables are staged in shared memory (18 KB per CTA: folded
+// bitmap + beam angles).  Everything per ego comes from k_features through L1/L2.
 template <int RT>   // RT = beam count known at compile time (72, 96) or 0 = run-time d.R
 __global__ void __launch_bounds__(LID_THREADS, ISX_LID_MINB)
 k_lidar_obs(const Dev d, int mode) {

@@ -301,7 +301,7 @@ ISX_HD void ray_pixel(float cx, float cy, float dx, float dy, int k, int& px, in
 //   bits : (HALF+1) rows x ROAD_WORDS u32, bit (u,v) = on_road(375+-u, 375+-v)  (the map is mirror-symmetric)
 //   skip : (SKIP_DIM x SKIP_DIM) u8 per 4x4 block of (u,v): samples that can be skipped for sure
 constexpr int ROAD_HALF = 375;               // u,v in [0,375]
-constexpr int ROAD_WORDS = 12;               // 376 bits -> 12 words (18 KB: 8 CTAs of k_lidar_obs fit one SM)
+constexpr int ROAD_WORDS = 12;               // 376 bits -> 12 words (18 KB per CTA of k_lidar_obs)
 constexpr int ROAD_ROWS = ROAD_HALF + 1;
 constexpr int SKIP_DIM = 94;                 // ceil(376/4)
 
@@ -349,7 +349,9 @@ ISX_HD float axis_exit(float c, float d, float inv_d, int lo, int hi) {
     return INFINITY;
 }
 
-// ---- road march.  State of one ray: the last sample known NOT to be an event (k, px, py), or the result.
+// ---- road march.  (march_step / ray_road_event below are the round-1 skip-table + strip-box march: no kernel uses them any
+// more; the host build keeps them as the independent reference the analytic march is validated against — isxh_road_events,
+// tests/test_host_units.py.)  State of one ray: the last sample known NOT to be an event (k, px, py), or the result.
 //   done && hit   : off-road pixel at sample ke  (Lidar.cpp:44-48)
 //   done && !hit  : left the screen at sample ke (:38-40), or ke == 63: nothing within range
 //   ke == 0       : the origin pixel itself is off screen (the reference breaks at dist 0)
@@ -470,8 +472,8 @@ ISX_HD int ray_safe_samples(const RoadAna& ra, const Ray& r) {
     return !ra.enabled ? 0 : (k < 0 ? 0 : (k > LIDAR_MAX_K ? LIDAR_MAX_K : k));
 }
 
-// One exact step of the march after the analytic jump: the next sample (plus what the skip table of the last TESTED pixel
-// allows, when there is one) is tested with the exact arithmetic of Lidar.cpp:34-46.
+// One exact step of the march after the analytic jump: the next sample is tested with the exact arithmetic of
+// Lidar.cpp:34-46.
 ISX_HD void march_next(const uint32_t* bits, const Ray& r, March& m) {
     m.k += 1;
     if (m.k > LIDAR_MAX_K) { m.ke = LIDAR_MAX_K + 1; m.done = true; return; }
