@@ -335,9 +335,10 @@ struct Ray {
 ISX_HD Ray make_ray(float cx, float cy, float dx, float dy) {
     Ray r;
     r.cx = cx; r.cy = cy; r.dx = dx; r.dy = dy;
-    // only used for conservative bounds (0.01 px of slack against ~1e-7 relative error): approximate is fine
-    r.inv_dx = (dx != 0.0f) ? approx_rcp(dx) : 0.0f;
-    r.inv_dy = (dy != 0.0f) ? approx_rcp(dy) : 0.0f;
+    // only used for conservative bounds (0.01 px of slack against ~1e-7 relative error): approximate is fine.  A component
+    // of (almost) zero gets a finite reciprocal of its sign (the coordinate then moves < 3e-4 px over the whole ray).
+    r.inv_dx = (fabsf(dx) > 1e-6f) ? approx_rcp(dx) : copysignf(1e6f, dx);
+    r.inv_dy = (fabsf(dy) > 1e-6f) ? approx_rcp(dy) : copysignf(1e6f, dy);
     return r;
 }
 
@@ -497,41 +498,45 @@ ISX_HD int ray_road_event_ana(const RoadAna& ra, const uint32_t* bits, const Ray
 // candidates are then checked with the exact integer test, in order.  Only on-screen pixels can be hit
 // (the march breaks off screen first), so the rectangle is clamped to the screen; truncation toward zero
 // maps every value in (-1, 1) to pixel 0, hence the wider lower bound when the clamped edge is 0.
+ISX_HD int f2i_ceil(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_ru(x);
+#else
+    return (int)ceilf(x);
+#endif
+}
+ISX_HD int f2i_floor(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rd(x);
+#else
+    return (int)floorf(x);
+#endif
+}
 ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
     const float cx = ray.cx, cy = ray.cy, dx = ray.dx, dy = ray.dy;
     const int x0 = r.x0 < 0 ? 0 : r.x0, x1 = r.x1 > WIDTH - 1 ? WIDTH - 1 : r.x1;
     const int y0 = r.y0 < 0 ? 0 : r.y0, y1 = r.y1 > HEIGHT - 1 ? HEIGHT - 1 : r.y1;
     if (x0 > x1 || y0 > y1) return 0;
-    float t0 = 0.0f, t1 = (float)(4 * kmax) + 0.5f;
-    {
-        const float lo = (x0 == 0 ? -1.01f : (float)x0 - 0.01f) - cx, hi = ((float)x1 + 1.01f) - cx;
-        if (fabsf(dx) > 1e-6f) {
-            const float inv = ray.inv_dx;
-            float a = lo * inv, b = hi * inv;
-            if (a > b) { const float t = a; a = b; b = t; }
-            t0 = fmaxf(t0, a); t1 = fminf(t1, b);
-        } else if (lo > 0.01f || hi < -0.01f) return 0;
-    }
-    {
-        const float lo = (y0 == 0 ? -1.01f : (float)y0 - 0.01f) - cy, hi = ((float)y1 + 1.01f) - cy;
-        if (fabsf(dy) > 1e-6f) {
-            const float inv = ray.inv_dy;
-            float a = lo * inv, b = hi * inv;
-            if (a > b) { const float t = a; a = b; b = t; }
-            t0 = fmaxf(t0, a); t1 = fminf(t1, b);
-        } else if (lo > 0.01f || hi < -0.01f) return 0;
-    }
+    // Slab bounds per axis.  A direction component of (almost) zero needs no special case: make_ray gives it a finite
+    // reciprocal of magnitude >= 1e6, so an origin outside the bounds by more than 0.01 px maps to |t| >= 1e4 (empty
+    // bracket), one inside to an unconstrained bracket, and the 0.01 px in between is decided by the exact verification.
+    const float lox = (x0 == 0 ? -1.01f : (float)x0 - 0.01f) - cx, hix = ((float)x1 + 1.01f) - cx;
+    const float loy = (y0 == 0 ? -1.01f : (float)y0 - 0.01f) - cy, hiy = ((float)y1 + 1.01f) - cy;
+    const float ax = lox * ray.inv_dx, bx = hix * ray.inv_dx;
+    const float ay = loy * ray.inv_dy, by = hiy * ray.inv_dy;
+    const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), 0.0f);
+    const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), (float)(4 * kmax) + 0.5f);
     if (!(t0 <= t1)) return 0;
     // a sample inside the rectangle sits at least 0.0099 px inside the slab bounds (their 0.01 px of slack minus the
     // rounding of the sample position), so 4k lies strictly inside [t0, t1]: no extra candidate on either side
-    int ka = (int)ceilf(t0 * 0.25f);
-    int kb = (int)floorf(t1 * 0.25f);
+    int ka = f2i_ceil(t0 * 0.25f);
+    int kb = f2i_floor(t1 * 0.25f);
     if (ka < 1) ka = 1;
     if (kb > kmax) kb = kmax;
     for (int k = ka; k <= kb; ++k) {
         int px, py;
         ray_pixel(cx, cy, dx, dy, k, px, py);
-        if (px >= x0 && px <= x1 && py >= y0 && py <= y1) return k;
+        if ((unsigned)(px - x0) <= (unsigned)(x1 - x0) && (unsigned)(py - y0) <= (unsigned)(y1 - y0)) return k;
     }
     return 0;
 }
