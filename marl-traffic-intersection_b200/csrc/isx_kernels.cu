@@ -796,7 +796,7 @@ k_features(const Dev d, int mode) {
 // the rays are done after one test, 98.6% after two, 99.6% after three (tools/march_stats.py).  The few rays still open
 // (grazing a wall) are finished ONE AT A TIME by the whole warp, lane j testing sample k+1+j — so a warp never idles 31
 // lanes while one grazing ray crawls along a wall.
-__device__ __forceinline__ int warp_road_event(bool active, const uint32_t* bits, const RoadAna& ra, const Ray& r, bool* hit, int lane) {
+__device__ __forceinline__ int warp_road_event(bool active, const RoadBitsShared bits, const RoadAna& ra, const Ray& r, bool* hit, int lane) {
     March m;
     m.k = 0; m.px = 0; m.py = 0; m.ke = LIDAR_MAX_K + 1; m.done = true; m.hit = false;
     if (active) march_init(r, m);
@@ -852,6 +852,7 @@ k_lidar_obs(const Dev d, int mode) {
     }
     pdl_wait();                                      // k_features' records, candidate lists and the zeroed work counter
     __syncthreads();
+    const RoadBitsShared road_bits{(uint32_t)__cvta_generic_to_shared(s_bits)};
     const int CE = d.N + d.M;
     const int total = d.E * d.N * R;                 // < 2^31, checked by isx_create
     const AgentRec* recs = reinterpret_cast<const AgentRec*>(d.agent_rec);
@@ -890,7 +891,7 @@ k_lidar_obs(const Dev d, int mode) {
                     ray = make_ray(rec.x, rec.y, cs, -sn);
                 }
                 bool hit;
-                const int ke = warp_road_event(alive, s_bits, d.ana, ray, &hit, lane);
+                const int ke = warp_road_event(alive, road_bits, d.ana, ray, &hit, lane);
                 if (alive) {
                     int best = hit ? ke : 0;
                     int lim = ke - 1;                           // cars only count strictly before the road event

@@ -373,12 +373,36 @@ ISX_HD void march_init(const Ray& r, March& m) {
 }
 
 // Exact test of sample k: 0 = nothing, 1 = off screen (march breaks, no hit), 2 = off-road pixel (hit).
-ISX_HD int sample_event(const uint32_t* bits, const Ray& r, int k, int& px, int& py) {
+// `bits`: where the folded bitmap lives — a plain pointer, or (device) a shared-memory address read with ld.shared, which
+// spares every test the generic-to-shared window arithmetic a plain pointer into shared memory costs.
+struct RoadBitsPtr {
+    const uint32_t* p;
+    ISX_HDM uint32_t word(int i) const { return p[i]; }
+};
+#if defined(__CUDACC__)
+struct RoadBitsShared {
+    uint32_t addr;                                   // __cvta_generic_to_shared of the table
+    __device__ __forceinline__ uint32_t word(int i) const {
+        uint32_t w;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr + 4u * (uint32_t)i));
+        return w;
+    }
+};
+#endif
+ISX_HD int iabs_(int x) { return x < 0 ? -x : x; }
+template <class B>
+ISX_HD int sample_event(const B& bits, const Ray& r, int k, int& px, int& py) {
     ray_pixel(r.cx, r.cy, r.dx, r.dy, k, px, py);
     if ((unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT) return 1;
-    int u = px - ROAD_HALF; u = u < 0 ? -u : u;
-    int v = py - ROAD_HALF; v = v < 0 ? -v : v;
-    return ((bits[v * ROAD_WORDS + (u >> 5)] >> (u & 31)) & 1u) ? 0 : 2;
+#if defined(__CUDA_ARCH__)
+    const int u = abs(px - ROAD_HALF), v = abs(py - ROAD_HALF);
+#else
+    const int u = iabs_(px - ROAD_HALF), v = iabs_(py - ROAD_HALF);
+#endif
+    return ((bits.word(v * ROAD_WORDS + (u >> 5)) >> (u & 31)) & 1u) ? 0 : 2;
+}
+ISX_HD int sample_event(const uint32_t* bits, const Ray& r, int k, int& px, int& py) {
+    return sample_event(RoadBitsPtr{bits}, r, k, px, py);
 }
 
 // One accelerated step from a non-event sample.  Exactness-preserving: two sources of "these samples cannot be
@@ -475,12 +499,14 @@ ISX_HD int ray_safe_samples(const RoadAna& ra, const Ray& r) {
 
 // One exact step of the march after the analytic jump: the next sample is tested with the exact arithmetic of
 // Lidar.cpp:34-46.
-ISX_HD void march_next(const uint32_t* bits, const Ray& r, March& m) {
+template <class B>
+ISX_HD void march_next(const B& bits, const Ray& r, March& m) {
     m.k += 1;
     if (m.k > LIDAR_MAX_K) { m.ke = LIDAR_MAX_K + 1; m.done = true; return; }
     const int e = sample_event(bits, r, m.k, m.px, m.py);
     if (e) { m.ke = m.k; m.hit = (e == 2); m.done = true; }
 }
+ISX_HD void march_next(const uint32_t* bits, const Ray& r, March& m) { march_next(RoadBitsPtr{bits}, r, m); }
 // Road event of one ray, sequential form of what the kernel does (analytic jump, then exact samples).
 ISX_HD int ray_road_event_ana(const RoadAna& ra, const uint32_t* bits, const Ray& r, bool* hit, int* tests = nullptr) {
     March m;
