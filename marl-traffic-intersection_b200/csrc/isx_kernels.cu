@@ -853,6 +853,7 @@ k_lidar_obs(const Dev d, int mode) {
     pdl_wait();                                      // k_features' records, candidate lists and the zeroed work counter
     __syncthreads();
     const RoadBitsShared road_bits{(uint32_t)__cvta_generic_to_shared(s_bits)};
+    const uint32_t rel_addr = (uint32_t)__cvta_generic_to_shared(s_rel);
     const int CE = d.N + d.M;
     const int total = d.E * d.N * R;                 // < 2^31, checked by isx_create
     const AgentRec* recs = reinterpret_cast<const AgentRec*>(d.agent_rec);
@@ -869,52 +870,58 @@ k_lidar_obs(const Dev d, int mode) {
         if (p0 >= pieces) break;
         const int p1 = min(p0 + WARP_GRAB, pieces);
         for (int pc = p0; pc < p1; ++pc) {
+            // all global indices below fit 32 unsigned bits (isx_create: E*N*96 < 2^31), so addresses are one
+            // base + 32-bit offset multiply-add each instead of 64-bit index arithmetic
             const int id = pc * 32 + lane;
             const bool valid = id < total;
-            const int ga = valid ? id / R : 0;
-            const int i = valid ? id - ga * R : 0;
+            const unsigned ga = valid ? (unsigned)(id / R) : 0u;
+            const int i = valid ? id - (int)ga * R : 0;
             const AgentRec rec = recs[ga];
-            const bool stored = valid && (mode == LIDAR_FROM_HITS ? rec.rect_base != -1 : rec.rect_base == -2);
             const bool alive = valid && rec.rect_base >= 0;
             float out = 0.0f;                                   // dead ego: all-zero row (:426-429)
             int kout = 0;                                       // hit index behind `out` (compact copy for the host-buffer step)
-            if (stored) {
-                const int k = d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i];
-                out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
-                kout = k;
+            // beams that are not marched (rare, so behind a warp-uniform branch): isx_observe / set_state refresh every live
+            // ego from the stored hits; so does an env that this call only reset in next-step auto-reset mode (rect_base == -2)
+            const bool stored = valid && (mode == LIDAR_FROM_HITS ? rec.rect_base != -1 : rec.rect_base == -2);
+            if (__any_sync(FULL, stored)) {
+                if (stored) {
+                    const int k = d.lidar_hit[ga * (unsigned)ISX_MAX_RAYS + (unsigned)i];
+                    out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
+                    kout = k;
+                }
             }
             if (mode != LIDAR_FROM_HITS) {
-                Ray ray = make_ray(0.0f, 0.0f, 1.0f, 0.0f);
-                if (alive) {
-                    float sn, cs;
-                    sincosf_(rec.h + s_rel[i], &sn, &cs);
-                    ray = make_ray(rec.x, rec.y, cs, -sn);
-                }
+                // every lane builds its ray from the record it loaded (lanes past the end read ego 0): dead or padding
+                // lanes are simply not marched, and no second, constant ray has to be materialised
+                float sn, cs, rel;
+                asm("ld.shared.f32 %0, [%1];" : "=f"(rel) : "r"(rel_addr + 4u * (unsigned)i));
+                sincosf_(rec.h + rel, &sn, &cs);
+                const Ray ray = make_ray(rec.x, rec.y, cs, -sn);
                 bool hit;
                 const int ke = warp_road_event(alive, road_bits, d.ana, ray, &hit, lane);
                 if (alive) {
                     int best = hit ? ke : 0;
                     int lim = ke - 1;                           // cars only count strictly before the road event
                     const int nc = d.cand_n[ga];
-                    const uint32_t* cand = d.cand + (size_t)ga * CE;
+                    const unsigned cbase = ga * (unsigned)CE;
                     const int iw = (i == R - 1) ? 0 : i;        // beam R-1 duplicates beam 0
                     for (int j = 0; j < nc && lim >= 1; ++j) {
-                        const uint32_t ci = cand[j];
+                        const uint32_t ci = d.cand[cbase + (unsigned)j];
                         if ((int)(ci >> 24) > lim) continue;     // the car lies beyond what this beam can still see (kmin)
                         int dlt = iw - (int)((ci >> 8) & 255u);  // angular window of this car (beam_window); span 255 = all
                         dlt += (dlt >> 31) & (R - 1);
                         if (dlt > (int)((ci >> 16) & 255u)) continue;
-                        const int kh = ray_rect_first_hit(rects[rec.rect_base + (int)(ci & 255u)], ray, lim);
+                        const int kh = ray_rect_first_hit(rects[(unsigned)rec.rect_base + (ci & 255u)], ray, lim);
                         if (kh) { best = kh; lim = kh - 1; }
                     }
-                    d.lidar_hit[(size_t)ga * ISX_MAX_RAYS + i] = (uint8_t)best;
+                    d.lidar_hit[ga * (unsigned)ISX_MAX_RAYS + (unsigned)i] = (uint8_t)best;
                     out = (best ? (float)(4 * best) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
                     kout = best;
                 }
             }
             if (valid) {
-                d.obs[(size_t)ga * ISX_OBS_DIM + 31 + i] = out;
-                d.hit_c[id] = (uint8_t)kout;                   // id == ga * R + i: one coalesced byte per lane
+                d.obs[ga * (unsigned)ISX_OBS_DIM + 31u + (unsigned)i] = out;
+                d.hit_c[(unsigned)id] = (uint8_t)kout;         // id == ga * R + i: one coalesced byte per lane
             }
         }
     }
