@@ -42,7 +42,7 @@ constexpr int DYN_WARPS = ISX_DYN_WARPS;   // envs (warps) per CTA in k_traffic
 constexpr int EGO_THREADS = ISX_EGO_THREADS;
 constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
 #ifndef ISX_LID_MINB
-#define ISX_LID_MINB 5      // 39 registers instead of 32: 844 -> 788 us at 65,536 envs (6: 818, 4: 807, 3: 808); the kernel is issue-bound, not latency-bound
+#define ISX_LID_MINB 4      // CTAs per SM: the kernel is issue-bound, not latency-bound, so registers beat occupancy (round-2 history: 8 -> 844 us, 5 -> 788; after the instruction trims 5 -> 716, 4 -> 710, 3 -> 712, 6 -> 770)
 #endif
 constexpr int LID_THREADS = 256;
 #ifndef ISX_TRAFFIC_LANES
@@ -50,7 +50,7 @@ constexpr int LID_THREADS = 256;
 #endif
 constexpr int TRAFFIC_LANES = ISX_TRAFFIC_LANES;   // lanes per env in k_traffic: 8 (four envs per warp), 16 or 32
 #ifndef ISX_WARP_GRAB
-#define ISX_WARP_GRAB 2
+#define ISX_WARP_GRAB 3
 #endif
 #ifndef ISX_LOCKSTEP
 #define ISX_LOCKSTEP 2
@@ -835,7 +835,7 @@ __device__ __forceinline__ int warp_road_event(bool active, const RoadBitsShared
 // One THREAD per (ego, beam), beams of all egos laid end to end; persistent CTAs walk 256-beam chunks, so the only
 // block-level synchronisation is the one after the road tables are staged in shared memory (18 KB per CTA: folded
 // bitmap + beam angles).  Everything per ego comes from k_features through L1/L2.
-template <int RT>   // RT = beam count known at compile time (72, 96) or 0 = run-time d.R
+template <int RT, bool WHOLE>   // RT = beam count known at compile time (72, 96) or 0 = run-time d.R; WHOLE: the beam total is a multiple of 32 (no padding lanes)
 __global__ void __launch_bounds__(LID_THREADS, ISX_LID_MINB)
 k_lidar_obs(const Dev d, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -873,7 +873,7 @@ k_lidar_obs(const Dev d, int mode) {
             // all global indices below fit 32 unsigned bits (isx_create: E*N*96 < 2^31), so addresses are one
             // base + 32-bit offset multiply-add each instead of 64-bit index arithmetic
             const int id = pc * 32 + lane;
-            const bool valid = id < total;
+            const bool valid = WHOLE || id < total;
             const unsigned ga = valid ? (unsigned)(id / R) : 0u;
             const int i = valid ? id - (int)ga * R : 0;
             const AgentRec rec = recs[ga];
@@ -1193,9 +1193,13 @@ cudaError_t launch_rays(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
     const long long chunks = (total + LID_THREADS - 1) / LID_THREADS;
     const int grid = (int)(chunks < grid_cap ? chunks : grid_cap);
     const size_t sm = lidar_smem_bytes(d);
-    if (d.R == 72) return launch_pdl(k_lidar_obs<72>, grid, LID_THREADS, sm, st, d, mode);
-    if (d.R == 96) return launch_pdl(k_lidar_obs<96>, grid, LID_THREADS, sm, st, d, mode);
-    return launch_pdl(k_lidar_obs<0>, grid, LID_THREADS, sm, st, d, mode);
+    if (total % 32 == 0) {
+        if (d.R == 72) return launch_pdl(k_lidar_obs<72, true>, grid, LID_THREADS, sm, st, d, mode);
+        if (d.R == 96) return launch_pdl(k_lidar_obs<96, true>, grid, LID_THREADS, sm, st, d, mode);
+    }
+    if (d.R == 72) return launch_pdl(k_lidar_obs<72, false>, grid, LID_THREADS, sm, st, d, mode);
+    if (d.R == 96) return launch_pdl(k_lidar_obs<96, false>, grid, LID_THREADS, sm, st, d, mode);
+    return launch_pdl(k_lidar_obs<0, false>, grid, LID_THREADS, sm, st, d, mode);
 }
 cudaError_t launch_lidar_obs(const Dev& d, int mode, int grid_cap, cudaStream_t st) {
     cudaError_t e = launch_features(d, mode, st);
@@ -1234,15 +1238,20 @@ cudaError_t launch_math_probe(int n, const float* a, const float* b, float* sn, 
 }
 cudaError_t lidar_set_smem_attr(const Dev& d) {
     const int b = (int)lidar_smem_bytes(d);
-    cudaError_t e = cudaFuncSetAttribute(k_lidar_obs<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    cudaError_t e = cudaFuncSetAttribute(k_lidar_obs<72, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<72, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lidar_obs<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
     return e;
 }
 cudaError_t lidar_occupancy(const Dev& d, int* ctas_per_sm) {
-    if (d.R == 72) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<72>, LID_THREADS, lidar_smem_bytes(d));
-    if (d.R == 96) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<96>, LID_THREADS, lidar_smem_bytes(d));
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<0>, LID_THREADS, lidar_smem_bytes(d));
+    const bool whole = ((long long)d.E * d.N * d.R) % 32 == 0;     // the instance launch_rays picks
+    if (whole && d.R == 72) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<72, true>, LID_THREADS, lidar_smem_bytes(d));
+    if (whole && d.R == 96) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<96, true>, LID_THREADS, lidar_smem_bytes(d));
+    if (d.R == 72) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<72, false>, LID_THREADS, lidar_smem_bytes(d));
+    if (d.R == 96) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<96, false>, LID_THREADS, lidar_smem_bytes(d));
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_lidar_obs<0, false>, LID_THREADS, lidar_smem_bytes(d));
 }
 
 }  // namespace isx
