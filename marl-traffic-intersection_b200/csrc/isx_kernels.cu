@@ -590,7 +590,8 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
 // (Lidar.cpp:65-78 as integer bounds) and, per ego, the packed list of cars a beam can possibly touch together with
 // the angular beam window of each (beam_window).  Cheap (<2% of the step): thread-per-ego, no shared memory.
 enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
-struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE; -1: dead ego (zero row); -2: beams come from the stored hits
+struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE; -1: dead ego (zero row); -2: beams come from the stored hits;
+                                                       // -3: the origin pixel is off screen (every beam breaks at distance 0, Lidar.cpp:38-40)
 
 // Rare path of k_features: the reference's neighbour list of one ego (other alive egos in index order, then the NPCs in
 // list order, :466-488), ordered by the restated libstdc++ std::sort; returns the car index (ego j, or N + NPC j; 0xff = none) of ranks 0..4,
@@ -644,7 +645,8 @@ k_features(const Dev d, int mode) {
     const bool fresh = d.auto_reset == 2 && mode == LIDAR_MARCH && d.step_count[env] == 0;
     if (ok && q == 0) {
         AgentRec rec;
-        rec.x = me.x; rec.y = me.y; rec.h = me.h; rec.rect_base = alive ? (fresh ? -2 : env * CE) : -1;
+        const bool off = (unsigned)f2i_rz(me.x) >= (unsigned)WIDTH || (unsigned)f2i_rz(me.y) >= (unsigned)HEIGHT;   // int(cx + dx * 0) of every beam
+        rec.x = me.x; rec.y = me.y; rec.h = me.h; rec.rect_base = alive ? (fresh ? -2 : (off ? -3 : env * CE)) : -1;
         reinterpret_cast<AgentRec*>(d.agent_rec)[ga] = rec;
     }
     float bd[5]; int bk[5];
@@ -797,11 +799,9 @@ k_features(const Dev d, int mode) {
 // (grazing a wall) are finished ONE AT A TIME by the whole warp, lane j testing sample k+1+j — so a warp never idles 31
 // lanes while one grazing ray crawls along a wall.
 __device__ __forceinline__ int warp_road_event(bool active, const RoadBitsShared bits, const RoadAna& ra, const Ray& r, bool* hit, int lane) {
-    March m;
-    m.k = 0; m.px = 0; m.py = 0; m.ke = LIDAR_MAX_K + 1; m.done = true; m.hit = false;
-    if (active) march_init(r, m);
-    const int ks = ray_safe_samples(ra, r);
-    if (!m.done) m.k = ks;
+    March m;                                         // the origin pixel is on screen (k_features sorts the other egos out)
+    m.px = 0; m.py = 0; m.ke = LIDAR_MAX_K + 1; m.done = !active; m.hit = false;
+    m.k = ray_safe_samples(ra, r);
 #pragma unroll
     for (int it = 0; it < LOCKSTEP; ++it)
         if (!m.done) march_next(bits, r, m);
@@ -835,6 +835,17 @@ __device__ __forceinline__ int warp_road_event(bool active, const RoadBitsShared
 // One THREAD per (ego, beam), beams of all egos laid end to end; persistent CTAs walk 256-beam chunks, so the only
 // block-level synchronisation is the one after the road tables are staged in shared memory (18 KB per CTA: folded
 // bitmap + beam angles).  Everything per ego comes from k_features through L1/L2.
+// Rare path of k_lidar_obs, out of line so that its address arithmetic is not predicated into every piece: a beam whose
+// value comes from the stored hit (refresh modes), or — off-screen origin — is "nothing within range" by definition.
+__device__ __noinline__ void unmarched_beam(const Dev& d, bool special, bool offscreen, unsigned hit_index, float& out, int& kout) {
+    if (!special) return;
+    int k = 0;
+    if (offscreen) d.lidar_hit[hit_index] = 0;
+    else k = d.lidar_hit[hit_index];
+    out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
+    kout = k;
+}
+
 template <int RT, bool WHOLE>   // RT = beam count known at compile time (72, 96) or 0 = run-time d.R; WHOLE: the beam total is a multiple of 32 (no padding lanes)
 __global__ void __launch_bounds__(LID_THREADS, ISX_LID_MINB)
 k_lidar_obs(const Dev d, int mode) {
@@ -880,16 +891,11 @@ k_lidar_obs(const Dev d, int mode) {
             const bool alive = valid && rec.rect_base >= 0;
             float out = 0.0f;                                   // dead ego: all-zero row (:426-429)
             int kout = 0;                                       // hit index behind `out` (compact copy for the host-buffer step)
-            // beams that are not marched (rare, so behind a warp-uniform branch): isx_observe / set_state refresh every live
-            // ego from the stored hits; so does an env that this call only reset in next-step auto-reset mode (rect_base == -2)
-            const bool stored = valid && (mode == LIDAR_FROM_HITS ? rec.rect_base != -1 : rec.rect_base == -2);
-            if (__any_sync(FULL, stored)) {
-                if (stored) {
-                    const int k = d.lidar_hit[ga * (unsigned)ISX_MAX_RAYS + (unsigned)i];
-                    out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
-                    kout = k;
-                }
-            }
+            // beams that are not marched (rare, so behind a warp-uniform branch): isx_observe / set_state refresh every live ego
+            // from the stored hits; so does an env that this call only reset in next-step auto-reset mode (rect_base == -2); an
+            // ego whose origin pixel is off screen reads \"nothing within range\" on every beam (-3)
+            const bool special = valid && (mode == LIDAR_FROM_HITS ? rec.rect_base != -1 : rec.rect_base < -1);
+            if (__any_sync(FULL, special)) unmarched_beam(d, special, mode != LIDAR_FROM_HITS && rec.rect_base == -3, ga * (unsigned)ISX_MAX_RAYS + (unsigned)i, out, kout);
             if (mode != LIDAR_FROM_HITS) {
                 // every lane builds its ray from the record it loaded (lanes past the end read ego 0): dead or padding
                 // lanes are simply not marched, and no second, constant ray has to be materialised

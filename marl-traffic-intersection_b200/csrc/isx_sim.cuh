@@ -468,16 +468,23 @@ ISX_HD float approx_sqrt(float x) {
     return sqrtf(x);
 #endif
 }
-ISX_HD float slab_time(float a, float d, float inv_d, float g) {           // first t >= 0 with a + d t >= g
-    return (a >= g) ? 0.0f : ((d > 0.0f) ? (g - a) * inv_d : INFINITY);
+// Per axis, with af = the coordinate along the ray's own direction of travel: the wall ahead (af >= g) is reached at
+// (g - af) / |d| (0 if already behind it); the wall behind (-af >= g) only counts if the origin is already past it.
+ISX_HD void slab_times(float a, float d, float inv_d, float g, float& t_first, float& t_other, bool& first_is_positive_side) {
+    const bool fwd = d > 0.0f;
+    const float af = fwd ? a : -a;
+    const float t_f = fmaxf((g - af) * fabsf(inv_d), 0.0f);      // d == 0: |inv_d| = 1e6, i.e. never unless already there
+    const float t_b = (-af >= g) ? 0.0f : INFINITY;
+    const bool f_first = t_f <= t_b;
+    t_first = f_first ? t_f : t_b; t_other = f_first ? t_b : t_f;
+    first_is_positive_side = f_first == fwd;
 }
 ISX_HD int ray_safe_samples(const RoadAna& ra, const Ray& r) {
     const float a = r.cx - (float)ROAD_HALF, b = r.cy - (float)ROAD_HALF;
-    const float tR = slab_time(a, r.dx, r.inv_dx, ra.g), tL = slab_time(-a, -r.dx, -r.inv_dx, ra.g);
-    const float tD = slab_time(b, r.dy, r.inv_dy, ra.g), tU = slab_time(-b, -r.dy, -r.inv_dy, ra.g);
-    const bool right = tR <= tL, down = tD <= tU;
-    const float tx = right ? tR : tL, txo = right ? tL : tR;
-    const float ty = down ? tD : tU, tyo = down ? tU : tD;
+    float tx, txo, ty, tyo;
+    bool right, down;
+    slab_times(a, r.dx, r.inv_dx, ra.g, tx, txo, right);
+    slab_times(b, r.dy, r.inv_dy, ra.g, ty, tyo, down);
     const float ts = fmaxf(tx, ty);
     const float t2 = fminf(fmaxf(txo, ty), fmaxf(tx, tyo));                // earliest slab time of the other three blobs
     float entry = ts;
