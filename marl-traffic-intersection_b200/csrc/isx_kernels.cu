@@ -590,7 +590,7 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
 // (Lidar.cpp:65-78 as integer bounds) and, per ego, the packed list of cars a beam can possibly touch together with
 // the angular beam window of each (beam_window).  Cheap (<2% of the step): thread-per-ego, no shared memory.
 enum { LIDAR_MARCH = 0, LIDAR_FROM_HITS = 1 };
-struct AgentRec { float x, y, h; int rect_base; };     // rect_base = env * CE; -1: dead ego (zero row); -2: beams come from the stored hits;
+struct alignas(16) AgentRec { float x, y, h; int rect_base; };     // (one 16-byte load) rect_base = env * CE; -1: dead ego (zero row); -2: beams come from the stored hits;
                                                        // -3: the origin pixel is off screen (every beam breaks at distance 0, Lidar.cpp:38-40)
 
 // Rare path of k_features: the reference's neighbour list of one ego (other alive egos in index order, then the NPCs in
@@ -837,13 +837,10 @@ __device__ __forceinline__ int warp_road_event(bool active, const RoadBitsShared
 // bitmap + beam angles).  Everything per ego comes from k_features through L1/L2.
 // Rare path of k_lidar_obs, out of line so that its address arithmetic is not predicated into every piece: a beam whose
 // value comes from the stored hit (refresh modes), or — off-screen origin — is "nothing within range" by definition.
-__device__ __noinline__ void unmarched_beam(const Dev& d, bool special, bool offscreen, unsigned hit_index, float& out, int& kout) {
-    if (!special) return;
-    int k = 0;
-    if (offscreen) d.lidar_hit[hit_index] = 0;
-    else k = d.lidar_hit[hit_index];
-    out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST);
-    kout = k;
+__device__ __noinline__ int unmarched_hit(const Dev& d, bool special, bool offscreen, unsigned hit_index) {
+    if (!special) return -1;
+    if (offscreen) { d.lidar_hit[hit_index] = 0; return 0; }
+    return d.lidar_hit[hit_index];
 }
 
 template <int RT, bool WHOLE>   // RT = beam count known at compile time (72, 96) or 0 = run-time d.R; WHOLE: the beam total is a multiple of 32 (no padding lanes)
@@ -895,7 +892,10 @@ k_lidar_obs(const Dev d, int mode) {
             // from the stored hits; so does an env that this call only reset in next-step auto-reset mode (rect_base == -2); an
             // ego whose origin pixel is off screen reads \"nothing within range\" on every beam (-3)
             const bool special = valid && (mode == LIDAR_FROM_HITS ? rec.rect_base != -1 : rec.rect_base < -1);
-            if (__any_sync(FULL, special)) unmarched_beam(d, special, mode != LIDAR_FROM_HITS && rec.rect_base == -3, ga * (unsigned)ISX_MAX_RAYS + (unsigned)i, out, kout);
+            if (__any_sync(FULL, special)) {
+                const int k = unmarched_hit(d, special, mode != LIDAR_FROM_HITS && rec.rect_base == -3, ga * (unsigned)ISX_MAX_RAYS + (unsigned)i);
+                if (k >= 0) { out = (k ? (float)(4 * k) : LIDAR_MAX_DIST) * (1.0f / LIDAR_MAX_DIST); kout = k; }
+            }
             if (mode != LIDAR_FROM_HITS) {
                 // every lane builds its ray from the record it loaded (lanes past the end read ego 0): dead or padding
                 // lanes are simply not marched, and no second, constant ray has to be materialised
@@ -914,9 +914,9 @@ k_lidar_obs(const Dev d, int mode) {
                     for (int j = 0; j < nc && lim >= 1; ++j) {
                         const uint32_t ci = d.cand[cbase + (unsigned)j];
                         if ((int)(ci >> 24) > lim) continue;     // the car lies beyond what this beam can still see (kmin)
-                        int dlt = iw - (int)((ci >> 8) & 255u);  // angular window of this car (beam_window); span 255 = all
+                        int dlt = iw - (int)__byte_perm(ci, 0u, 0x4441u);  // angular window of this car (beam_window); span 255 = all
                         dlt += (dlt >> 31) & (R - 1);
-                        if (dlt > (int)((ci >> 16) & 255u)) continue;
+                        if (dlt > (int)__byte_perm(ci, 0u, 0x4442u)) continue;
                         const int kh = ray_rect_first_hit(rects[(unsigned)rec.rect_base + (ci & 255u)], ray, lim);
                         if (kh) { best = kh; lim = kh - 1; }
                     }
