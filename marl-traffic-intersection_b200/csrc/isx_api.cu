@@ -195,7 +195,7 @@ static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
     s.epidx += oEN; s.ealive += oEN;
     s.nx += oEM; s.ny += oEM; s.nv += oEM; s.nh += oEM; s.nsteer += oEM; s.npidx += oEM; s.nroute += oEM; s.nuid += oEM;
     s.ncount += oE; s.next_uid += oE; s.step_count += oE; s.tick += oE;
-    s.agent_rec = static_cast<char*>(d.agent_rec) + oEN * 16; s.car_rect = static_cast<char*>(d.car_rect) + oEC * 16;
+    s.agent_rec = static_cast<char*>(d.agent_rec) + oEN * 16; s.car_rect = static_cast<char*>(d.car_rect) + oEC * sizeof(PixRect);
     s.cand += oEN * (size_t)(d.N + d.M); s.cand_n += oEN; s.ray_counter = d.ray_counter + shard_idx;
     s.obs_c += oEN * 32; s.hit_c += oEN * (size_t)d.R;
     s.obs += oEN * ISX_OBS_DIM; s.reward += oEN; s.done += oEN; s.status += oEN;
@@ -242,7 +242,7 @@ static std::vector<std::pair<void*, unsigned>> snapshot_arrays(const Dev& d) {
     v.push_back({d.obs, 4u * N * ISX_OBS_DIM}); v.push_back({d.reward, 4u * N}); v.push_back({d.done, N}); v.push_back({d.status, N});
     v.push_back({d.terminated, 1u}); v.push_back({d.truncated, 1u}); v.push_back({d.agents_alive, 4u});
     v.push_back({d.lidar_hit, N * ISX_MAX_RAYS}); v.push_back({d.events, (unsigned)sizeof(isx_traffic_events)});
-    v.push_back({d.car_rect, 16u * (N + M)});
+    v.push_back({d.car_rect, (unsigned)sizeof(PixRect) * (N + M)});
     return v;
 }
 
@@ -432,7 +432,7 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
     ALLOC(h->d_actions, EN * 2);
     if (getenv("ISX_TRACE")) ALLOC(d.trace, E * 16); else d.trace = nullptr;
     {
-        float4* rec; int4* rc;
+        float4* rec; PixRect* rc;
         ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN);
         ALLOC(d.ray_counter, ISX_MAX_GROUPS + 8);
         d.agent_rec = rec; d.car_rect = rc;

@@ -674,7 +674,7 @@ k_features(const Dev d, int mode) {
             const bool same = fabsf(ox - me.x) < 1e-3f && fabsf(oy - me.y) < 1e-3f && fabsf(oh - me.h) < 1e-3f;
             if (!same) {
                 const PixRect r = rects[k];        // written by k_ego / k_traffic earlier in this step
-                is_cand = !(r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250);
+                is_cand = !(r.x0 > ipx + 250 || r.x1 < ipx - 250 || r.y0 > ipy + 250 || r.y1 < ipy - 250) && !pix_rect_empty(r);   // (clamped to the screen)
             }
         }
         const unsigned qb = (__ballot_sync(FULL, is_cand) >> qshift) & 0xFu;      // this quad's votes, in car order

@@ -277,17 +277,28 @@ ISX_HD float reward_base(const RewardCfg& rc, float x, float y, float v, float a
 // ---------------------------------------------------------------- lidar (Lidar.cpp:16-90)
 // Integer pixel rectangle equivalent to the float AABB test of Lidar.cpp:65-78:
 //   float(px) >= c.x - ex  &&  float(px) <= c.x + ex   <=>   ceil(c.x - ex) <= px <= floor(c.x + ex)
-struct PixRect { int x0, x1, y0, y1; };
+// The record also carries what every beam test needs from it (ray_rect_first_hit): the rectangle CLAMPED to the screen —
+// only on-screen pixels can be hit, the march breaks off screen first — and the slab bounds of the real sample positions
+// that truncate into it (0.01 px of slack; truncation toward zero maps every value in (-1, 1) to pixel 0, hence the wider
+// lower bound when the clamped edge is 0).  A rectangle that is empty after clamping gets bounds no ray satisfies.
+struct alignas(16) PixRect { int x0, x1, y0, y1; float lox, hix, loy, hiy; };
+ISX_HD PixRect make_pix_rect(int x0, int x1, int y0, int y1) {
+    PixRect r;
+    r.x0 = x0 < 0 ? 0 : x0; r.x1 = x1 > WIDTH - 1 ? WIDTH - 1 : x1;
+    r.y0 = y0 < 0 ? 0 : y0; r.y1 = y1 > HEIGHT - 1 ? HEIGHT - 1 : y1;
+    if (r.x0 > r.x1 || r.y0 > r.y1) { r.lox = r.hix = r.loy = r.hiy = 1e30f; return r; }
+    r.lox = r.x0 == 0 ? -1.01f : (float)r.x0 - 0.01f; r.hix = (float)r.x1 + 1.01f;
+    r.loy = r.y0 == 0 ? -1.01f : (float)r.y0 - 0.01f; r.hiy = (float)r.y1 + 1.01f;
+    return r;
+}
+ISX_HD bool pix_rect_empty(const PixRect& r) { return r.x0 > r.x1 || r.y0 > r.y1; }
 ISX_HD_NOINL PixRect car_pixel_rect(float x, float y, float h) {
     float s, c;
     sincosf_nc(h, &s, &c);
     const float hl = CAR_LENGTH * 0.5f, hw = CAR_WIDTH * 0.5f;
     const float ex = fabsf(c) * hl + fabsf(s) * hw;
     const float ey = fabsf(s) * hl + fabsf(c) * hw;
-    PixRect r;
-    r.x0 = (int)ceilf(x - ex); r.x1 = (int)floorf(x + ex);
-    r.y0 = (int)ceilf(y - ey); r.y1 = (int)floorf(y + ey);
-    return r;
+    return make_pix_rect((int)ceilf(x - ex), (int)floorf(x + ex), (int)ceilf(y - ey), (int)floorf(y + ey));
 }
 
 // Pixel of sample k on a ray (Lidar.cpp:34-35): mul and add rounded separately, truncation toward 0.
@@ -547,16 +558,12 @@ ISX_HD int f2i_floor(float x) {
 }
 ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
     const float cx = ray.cx, cy = ray.cy, dx = ray.dx, dy = ray.dy;
-    const int x0 = r.x0 < 0 ? 0 : r.x0, x1 = r.x1 > WIDTH - 1 ? WIDTH - 1 : r.x1;
-    const int y0 = r.y0 < 0 ? 0 : r.y0, y1 = r.y1 > HEIGHT - 1 ? HEIGHT - 1 : r.y1;
-    if (x0 > x1 || y0 > y1) return 0;
-    // Slab bounds per axis.  A direction component of (almost) zero needs no special case: make_ray gives it a finite
-    // reciprocal of magnitude >= 1e6, so an origin outside the bounds by more than 0.01 px maps to |t| >= 1e4 (empty
-    // bracket), one inside to an unconstrained bracket, and the 0.01 px in between is decided by the exact verification.
-    const float lox = (x0 == 0 ? -1.01f : (float)x0 - 0.01f) - cx, hix = ((float)x1 + 1.01f) - cx;
-    const float loy = (y0 == 0 ? -1.01f : (float)y0 - 0.01f) - cy, hiy = ((float)y1 + 1.01f) - cy;
-    const float ax = lox * ray.inv_dx, bx = hix * ray.inv_dx;
-    const float ay = loy * ray.inv_dy, by = hiy * ray.inv_dy;
+    // Slab bounds per axis (prepared with the rectangle, see PixRect).  A direction component of (almost) zero needs no
+    // special case: make_ray gives it a finite reciprocal of magnitude >= 1e6, so an origin outside the bounds by more than
+    // 0.01 px maps to |t| >= 1e4 (empty bracket), one inside to an unconstrained bracket, and the 0.01 px in between is
+    // decided by the exact verification.  An empty rectangle has bounds of 1e30: the bracket is empty for every ray.
+    const float ax = (r.lox - cx) * ray.inv_dx, bx = (r.hix - cx) * ray.inv_dx;
+    const float ay = (r.loy - cy) * ray.inv_dy, by = (r.hiy - cy) * ray.inv_dy;
     const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), 0.0f);
     const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), (float)(4 * kmax) + 0.5f);
     if (!(t0 <= t1)) return 0;
@@ -569,7 +576,7 @@ ISX_HD int ray_rect_first_hit(const PixRect& r, const Ray& ray, int kmax) {
     for (int k = ka; k <= kb; ++k) {
         int px, py;
         ray_pixel(cx, cy, dx, dy, k, px, py);
-        if ((unsigned)(px - x0) <= (unsigned)(x1 - x0) && (unsigned)(py - y0) <= (unsigned)(y1 - y0)) return k;
+        if ((unsigned)(px - r.x0) <= (unsigned)(r.x1 - r.x0) && (unsigned)(py - r.y0) <= (unsigned)(r.y1 - r.y0)) return k;
     }
     return 0;
 }
