@@ -498,18 +498,17 @@ ISX_HD int ray_safe_samples(const RoadAna& ra, const Ray& r) {
     slab_times(b, r.dy, r.inv_dy, ra.g, ty, tyo, down);
     const float ts = fmaxf(tx, ty);
     const float t2 = fminf(fmaxf(txo, ty), fmaxf(tx, tyo));                // earliest slab time of the other three blobs
-    float entry = ts;
-    if (ts < 1000.0f) {
-        const float w1 = (right ? a : -a) - ra.U, w2 = (down ? b : -b) - ra.U;
-        const float d1 = right ? r.dx : -r.dx, d2 = down ? r.dy : -r.dy;
-        const float p1 = fmaf(d1, ts, w1), p2 = fmaf(d2, ts, w2);
-        if (p1 < -1e-3f && p2 < -1e-3f) {                                  // in the notch: only the quarter circle can be hit
-            const float B = fmaf(w1, d1, w2 * d2);
-            const float Cq = fmaf(w1, w1, fmaf(w2, w2, -ra.rho2));
-            const float D = fmaf(B, B, -Cq);
-            entry = (D < -0.05f) ? INFINITY : fmaxf(ts, -B - approx_sqrt(fmaxf(D, 0.0f)));
-        }
-    }
+    // straight-line on purpose: nearly every warp has a lane in the notch, so a branch would only add its own overhead
+    // (ts = inf makes p1 / p2 inf or NaN; every comparison with them is false and the refinement is not selected)
+    const float w1 = (right ? a : -a) - ra.U, w2 = (down ? b : -b) - ra.U;
+    const float d1 = right ? r.dx : -r.dx, d2 = down ? r.dy : -r.dy;
+    const float p1 = fmaf(d1, ts, w1), p2 = fmaf(d2, ts, w2);
+    const bool notch = ts < 1000.0f && p1 < -1e-3f && p2 < -1e-3f;         // in the notch: only the quarter circle can be hit
+    const float B = fmaf(w1, d1, w2 * d2);
+    const float Cq = fmaf(w1, w1, fmaf(w2, w2, -ra.rho2));
+    const float D = fmaf(B, B, -Cq);
+    const float refined = (D < -0.05f) ? INFINITY : fmaxf(ts, -B - approx_sqrt(fmaxf(D, 0.0f)));
+    float entry = notch ? refined : ts;
     entry = fminf(fminf(entry, t2), 1000.0f);
     const int k = (int)floorf((entry - 0.01f) * 0.25f);
     return !ra.enabled ? 0 : (k < 0 ? 0 : (k > LIDAR_MAX_K ? LIDAR_MAX_K : k));
