@@ -41,6 +41,9 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int DYN_WARPS = ISX_DYN_WARPS;   // envs (warps) per CTA in k_traffic
 constexpr int EGO_THREADS = ISX_EGO_THREADS;
 constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
+#ifndef ISX_TEST_BRANCHFREE
+#define ISX_TEST_BRANCHFREE 1
+#endif
 #ifndef ISX_LID_MINB
 #define ISX_LID_MINB 4      // CTAs per SM: the kernel is issue-bound, not latency-bound, so registers beat occupancy (round-2 history: 8 -> 844 us, 5 -> 788; after the instruction trims 5 -> 716, 4 -> 710, 3 -> 712, 6 -> 770)
 #endif
@@ -803,8 +806,26 @@ __device__ __forceinline__ int warp_road_event(bool active, const RoadBitsShared
     m.px = 0; m.py = 0; m.ke = LIDAR_MAX_K + 1; m.done = !active; m.hit = false;
     m.k = ray_safe_samples(ra, r);
 #pragma unroll
-    for (int it = 0; it < LOCKSTEP; ++it)
+    for (int it = 0; it < LOCKSTEP; ++it) {
+#if ISX_TEST_BRANCHFREE
+        // every lane evaluates the next sample (nearly every warp has an open ray anyway); done lanes discard the result.
+        // The sample index and the folded pixel are clamped so that the table read stays in range for discarded lanes.
+        const int k = min(m.k + 1, LIDAR_MAX_K);
+        int px, py;
+        ray_pixel(r.cx, r.cy, r.dx, r.dy, k, px, py);
+        const bool off = (unsigned)px >= (unsigned)WIDTH || (unsigned)py >= (unsigned)HEIGHT;
+        const int u = min(abs(px - ROAD_HALF), ROAD_HALF), v = min(abs(py - ROAD_HALF), ROAD_HALF);
+        const bool road = (bits.word(v * ROAD_WORDS + (u >> 5)) >> (u & 31)) & 1u;
+        const bool beyond = m.k + 1 > LIDAR_MAX_K;
+        const bool ev = beyond || off || !road;
+        if (!m.done) {
+            m.k += 1;
+            if (ev) { m.ke = beyond ? LIDAR_MAX_K + 1 : m.k; m.hit = !beyond && !off; m.done = true; }
+        }
+#else
         if (!m.done) march_next(bits, r, m);
+#endif
+    }
     unsigned pend = __ballot_sync(FULL, !m.done);
 #pragma unroll 1
     for (int it = 0; it < LOCKSTEP_EXTRA && __popc(pend) >= LOCKSTEP_MIN_OPEN; ++it) {
