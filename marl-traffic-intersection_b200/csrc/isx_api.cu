@@ -296,6 +296,8 @@ static int config_to_dev(const isx_config* cfg, Dev& d) {
     d.max_progress = hypotf_((float)WIDTH, (float)HEIGHT);
     d.seed = cfg->seed; d.env_base = cfg->env_id_base;
     if (d.traffic && d.T > 0 && (!cfg->traffic_start || !cfg->traffic_end)) return fail(ISX_E_ARG, "traffic routes missing");
+    d.traffic_lanes = 0;
+    if (const char* tl = getenv("ISX_TRAFFIC_LANES")) { const int v = atoi(tl); if (v == 8 || v == 16 || v == 32) d.traffic_lanes = v; }
     return ISX_OK;
 }
 

@@ -21,6 +21,7 @@ struct Dev {
     // ---- configuration
     int E, N, M, R, lanes;
     int use_team, respawn, max_steps, traffic, T, auto_reset;
+    int traffic_lanes;           // k_traffic lanes per env: 0 = by batch size, or 8 / 16 / 32 (ISX_TRAFFIC_LANES at isx_create; tests)
     RewardCfg rc;
     float max_progress;          // hypotf(750, 750)
     uint64_t seed;

@@ -49,9 +49,9 @@ constexpr int FEAT_THREADS = ISX_FEAT_THREADS;
 #endif
 constexpr int LID_THREADS = 256;
 #ifndef ISX_TRAFFIC_LANES
-#define ISX_TRAFFIC_LANES 8
+#define ISX_TRAFFIC_LANES 0     // 0: chosen per launch by batch size (launch_traffic)
 #endif
-constexpr int TRAFFIC_LANES = ISX_TRAFFIC_LANES;   // lanes per env in k_traffic: 8 (four envs per warp), 16 or 32
+constexpr int TRAFFIC_LANES = ISX_TRAFFIC_LANES;   // lanes per env in k_traffic: 8 (four envs per warp), 16, 32, or 0 = by batch size
 #ifndef ISX_WARP_GRAB
 #define ISX_WARP_GRAB 3
 #endif
@@ -1182,11 +1182,16 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 
 cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_t st) {
     if (!d.traffic) return cudaSuccess;
-    if (TRAFFIC_LANES == 8) {                         // four envs per warp (wide fallback inside the kernel)
+    // lanes per env by batch size (ISX_TRAFFIC_LANES = 8 / 16 / 32 forces one): small batches are bound by the list-order chain
+    // of the busiest env, which is shortest with a whole warp per env (4096 envs: 23.6 us at 32 lanes, 28.2 at 16, 36.2 at 8);
+    // large batches by the warps to retire (32768 envs: 83.9 / 71.4 / 64.3 us); 8192 envs: 32.3 / 31.3 / 38.6
+    const int forced = TRAFFIC_LANES ? TRAFFIC_LANES : d.traffic_lanes;
+    const int lanes = forced ? forced : (d.E <= 4096 ? 32 : d.E <= 12288 ? 16 : 8);
+    if (lanes == 8) {                                 // four envs per warp (wide fallback inside the kernel)
         const int blocks = (d.E + 4 * DYN_WARPS - 1) / (4 * DYN_WARPS);
         return launch_pdl(k_traffic<8>, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
     }
-    if (TRAFFIC_LANES == 16) {                        // two envs per warp
+    if (lanes == 16) {                                // two envs per warp
         const int blocks = (d.E + 2 * DYN_WARPS - 1) / (2 * DYN_WARPS);
         return launch_pdl(k_traffic<16>, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);
     }

@@ -55,7 +55,11 @@ def test_route_following_reaches_success_and_terminates():
     b.close()
 
 
-def test_dense_traffic_npc_collisions_and_yielding():
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_dense_traffic_npc_collisions_and_yielding(lanes, monkeypatch):
+    """Every k_traffic instance (8 / 16 / 32 lanes per env; the library picks by batch size, ISX_TRAFFIC_LANES forces one) on
+    the same dense traffic: up to 13 NPCs per env, so the 8- and 16-lane instances also run their wide in-kernel fallback."""
+    monkeypatch.setenv("ISX_TRAFFIC_LANES", str(lanes))
     cfg = dict(num_envs=6, num_agents=1, num_lanes=3, ego_routes=[("IN_6", "OUT_2")], traffic_flow=True, traffic_density=30.0,
                npc_capacity=32)
     b, refs = make_pair(_benv(), cfg, seed=5)
@@ -316,11 +320,12 @@ def test_npc_capacity_overflow_is_counted_not_fatal():
     b.close()
 
 
-def test_full_eight_lane_group_matches_until_the_first_dropped_spawn():
-    """k_traffic gives an env 8 lanes (four envs per warp).  With npc_capacity = 8 there is no wide fallback: a group whose
+def test_full_eight_lane_group_matches_until_the_first_dropped_spawn(monkeypatch):
+    """k_traffic<8> gives an env 8 lanes (four envs per warp; forced here, small batches would get a warp per env).  With npc_capacity = 8 there is no wide fallback: a group whose
     8 lanes all hold an NPC must still match the reference bit for bit, up to the step at which the bounded list drops a
     spawn the reference's unbounded list would take (counted in npc_overflow; from there the two legitimately differ)."""
     import torch
+    monkeypatch.setenv("ISX_TRAFFIC_LANES", "8")
     cfg = dict(num_envs=8, num_agents=1, num_lanes=3, ego_routes=[("IN_6", "OUT_2")], traffic_flow=True, traffic_density=30.0,
                npc_capacity=8)
     b, refs = make_pair(_benv(), cfg, seed=11)
