@@ -892,12 +892,16 @@ k_lidar_obs(const Dev d, int mode) {
     // set the kernel time at 67% average occupancy.  Each warp now claims WARP_GRAB consecutive 32-beam pieces at a
     // time from one global counter (zeroed by k_features, which always runs just before) until the beams run out.
     const int pieces = (total + 31) / 32;
+    // pieces per claim: WARP_GRAB when every warp gets many claims; small batches (a few pieces per warp) claim one at a time,
+    // otherwise a third of the warps would do all the work
+    const int warps_total = (int)gridDim.x * (LID_THREADS / 32);
+    const int grab = pieces >= 12 * warps_total ? WARP_GRAB : (pieces >= 4 * warps_total ? 2 : 1);
     while (true) {
         int p0 = 0;
-        if (lane == 0) p0 = (int)atomicAdd(d.ray_counter, (unsigned)WARP_GRAB);
+        if (lane == 0) p0 = (int)atomicAdd(d.ray_counter, (unsigned)grab);
         p0 = __shfl_sync(FULL, p0, 0);
         if (p0 >= pieces) break;
-        const int p1 = min(p0 + WARP_GRAB, pieces);
+        const int p1 = min(p0 + grab, pieces);
         for (int pc = p0; pc < p1; ++pc) {
             // all global indices below fit 32 unsigned bits (isx_create: E*N*96 < 2^31), so addresses are one
             // base + 32-bit offset multiply-add each instead of 64-bit index arithmetic
