@@ -255,6 +255,10 @@ int isx_stats_reset(isx_handle *h);
 /* Tuning aid: with ISX_TRACE=1 in the environment at isx_create, k_traffic stamps clock64() at its phase boundaries
  * per env; this copies the [E][16] stamps out (slots 0..5 = phase boundaries, 6 = NPC count).  ISX_E_STATE when off. */
 int isx_trace_read(isx_handle *h, long long *out16_per_env);
+/* Debug aid: with ISX_GUARD=1 in the environment at isx_create every device buffer of the handle sits between two 4 KB red
+ * zones holding a canary byte; this counts the red zones that were written to (0 = no kernel stored outside its buffers).
+ * Synchronous.  ISX_E_STATE when guards are off. */
+int isx_debug_check_guards(isx_handle *h, int64_t *violations);
 /* Tuning aid: one host-buffer step (stream path) with CUDA events around every pipeline range; ms[4*i+0..3] = kernels
  * begin / kernels end / copy begin / copy end of range i, ms since the step began.  Returns the number of ranges. */
 int isx_pipe_timeline(isx_handle *h, float dt, void *stream, float *ms, int32_t cap_ranges);

@@ -76,7 +76,7 @@ EXPORTS = [
     "isx_step_pinned", "isx_host_views", "isx_host_views_aux", "isx_host_step_info", "isx_expand_obs_rows",
     "isx_rollout", "isx_rollout_timed", "isx_rollout_timed4", "isx_get_buffers", "isx_num_envs", "isx_num_agents", "isx_get_env_state", "isx_set_env_state",
     "isx_observe", "isx_render", "isx_snapshot_create", "isx_snapshot_save", "isx_snapshot_restore", "isx_snapshot_destroy",
-    "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_pipe_timeline", "isx_stats_device_ptrs", "isx_route", "isx_math_probe",
+    "isx_stats_read", "isx_stats_reset", "isx_trace_read", "isx_debug_check_guards", "isx_pipe_timeline", "isx_stats_device_ptrs", "isx_route", "isx_math_probe",
     "isx_set_lidar_rays", "isx_lidar_rays", "isx_set_reward", "isx_configure_episode", "isx_set_traffic_density",
     "isx_car_update", "isx_car_check_collision",
 ]
@@ -130,6 +130,7 @@ def load_library(path: str | None = None):
     lib.isx_stats_read.argtypes = [vp, C.POINTER(Stats)]
     lib.isx_stats_reset.argtypes = [vp]
     lib.isx_trace_read.argtypes = [vp, vp]
+    lib.isx_debug_check_guards.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.isx_pipe_timeline.argtypes = [vp, f32, vp, C.POINTER(f32), i32]
     lib.isx_stats_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), vp]
     lib.isx_set_lidar_rays.argtypes = [vp, i32]

@@ -249,6 +249,13 @@ class BatchedIntersectionEnv:
             out = tuple(np.array(x) for x in out)
         return out
 
+    def check_guards(self) -> int:
+        """Debug aid (ISX_GUARD=1 in the environment when the batch was created): number of red zones around the library's
+        device buffers that a kernel wrote into; 0 = no out-of-bounds store since creation (isx_debug_check_guards)."""
+        v = C.c_int64(-1)
+        _lib.check(self._lib, self._lib.isx_debug_check_guards(self._h, C.byref(v)))
+        return int(v.value)
+
     def host_step_bytes(self) -> Dict[str, Any]:
         """What one step_host() moves over PCIe and who completes the obs rows on the host (isx_host_step_info)."""
         a, b, t, r = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()

@@ -162,6 +162,8 @@ struct isx_handle {
     int device = 0;
     int lidar_grid = 0;
     std::vector<void*> allocs;
+    bool guard = false;                                  // ISX_GUARD=1: red zones around every device buffer
+    std::vector<std::pair<unsigned char*, size_t>> guarded;   // (user pointer, user bytes) of every guarded buffer
     // pinned staging for isx_step_host
     float* h_actions = nullptr; float* d_actions = nullptr;
     float* h_obs = nullptr; float* h_reward = nullptr;
@@ -210,14 +212,30 @@ static isx_handle::Group& group_of(isx_handle* h, int env) {
     return h->groups.back();
 }
 
+// Every device buffer of a handle.  With ISX_GUARD=1 in the environment at isx_create (debug aid; compute-sanitizer is not
+// available everywhere) each buffer sits between two 4 KB red zones filled with a canary byte; isx_debug_check_guards
+// reports how many red zones were written to — an out-of-bounds store of any kernel shows up there.
+constexpr size_t GUARD_BYTES = 4096;
+constexpr int GUARD_CANARY = 0xA5;
 template <class T>
 static int dev_alloc(isx_handle* h, T** p, size_t n, bool zero = true) {
     void* q = nullptr;
     const size_t bytes = sizeof(T) * (n ? n : 1);
-    CK(cudaMalloc(&q, bytes));
-    if (zero) CK(cudaMemset(q, 0, bytes));
+    if (!h->guard) {
+        CK(cudaMalloc(&q, bytes));
+        if (zero) CK(cudaMemset(q, 0, bytes));
+        h->allocs.push_back(q);
+        *p = static_cast<T*>(q);
+        return 0;
+    }
+    const size_t padded = (bytes + 255) & ~(size_t)255;              // keep the user pointer 256-byte aligned
+    CK(cudaMalloc(&q, padded + 2 * GUARD_BYTES));
+    CK(cudaMemset(q, GUARD_CANARY, padded + 2 * GUARD_BYTES));
+    unsigned char* user = static_cast<unsigned char*>(q) + GUARD_BYTES;
+    if (zero) CK(cudaMemset(user, 0, bytes));
     h->allocs.push_back(q);
-    *p = static_cast<T*>(q);
+    h->guarded.push_back({user, bytes});
+    *p = reinterpret_cast<T*>(user);
     return 0;
 }
 
@@ -335,6 +353,7 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
     CK(cudaSetDevice(cfgs[0].device));
 
     isx_handle* h = new isx_handle();
+    { const char* g_ = getenv("ISX_GUARD"); h->guard = g_ && g_[0] == '1'; }
     h->device = cfgs[0].device;
     Dev& d = h->d;                      // the whole batch: group 0's settings, every env, the shared stride M
     d = gd[0];
@@ -1134,6 +1153,37 @@ int isx_stats_read(isx_handle* h, isx_stats* out) {
     out->neighbor_tie_sorts = (int64_t)raw[ST_TIESORT];
     return ISX_OK;
 }
+// Debug aid (ISX_GUARD=1 at isx_create): counts the red zones around the handle's device buffers that no longer hold the
+// canary.  *violations = 0 means no kernel stored outside its buffers since isx_create.  ISX_E_STATE when guards are off.
+int isx_debug_check_guards(isx_handle* h, int64_t* violations) {
+    if (!h || !violations) return fail(ISX_E_ARG, "null argument");
+    if (!h->guard) return fail(ISX_E_STATE, "guards are off (set ISX_GUARD=1 before isx_create)");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned char> zone(GUARD_BYTES);
+    int64_t bad = 0;
+    for (const auto& g : h->guarded) {
+        const size_t padded = (g.second + 255) & ~(size_t)255;
+        const unsigned char* zones[2] = {g.first - GUARD_BYTES, g.first + padded};
+        for (int z = 0; z < 2; ++z) {
+            CK(cudaMemcpy(zone.data(), zones[z], GUARD_BYTES, cudaMemcpyDeviceToHost));
+            bool hit = false;
+            for (size_t i = 0; i < GUARD_BYTES && !hit; ++i) hit = zone[i] != (unsigned char)GUARD_CANARY;
+            bad += hit ? 1 : 0;
+        }
+        // the alignment padding between the end of the buffer and the upper red zone is canary, too
+        if (padded > g.second) {
+            std::vector<unsigned char> pad(padded - g.second);
+            CK(cudaMemcpy(pad.data(), g.first + g.second, pad.size(), cudaMemcpyDeviceToHost));
+            bool hit = false;
+            for (unsigned char c : pad) hit = hit || c != (unsigned char)GUARD_CANARY;
+            bad += hit ? 1 : 0;
+        }
+    }
+    *violations = bad;
+    return ISX_OK;
+}
+
 int isx_trace_read(isx_handle* h, long long* out16_per_env) {
     if (!h || !out16_per_env) return fail(ISX_E_ARG, "null argument");
     if (!h->d.trace) return fail(ISX_E_STATE, "tracing is off (set ISX_TRACE=1 before isx_create)");

@@ -169,3 +169,67 @@ def test_runtime_lidar_rays_and_live_settings():
         r._f("configure_traffic")(r._h, 1, 6.0)
     run(80, "reconfigured")
     b.close()
+
+
+@pytest.mark.parametrize("shape", ["odd_sizes_traffic", "max_agents_generic_rays", "two_lanes_96"])
+def test_no_kernel_stores_outside_its_buffers(shape, monkeypatch):
+    """compute-sanitizer is not available on this GPU pool, so the library brings its own check: with ISX_GUARD=1 every
+    device buffer sits between red zones; after exercising every kernel and every mode on awkward sizes (env counts that
+    fill no warp, the maximum ego and NPC counts, beam counts that fill no piece, masked reset, snapshot / restore,
+    observe, both transports of the host step) no red zone may have been written to."""
+    import torch
+    monkeypatch.setenv("ISX_GUARD", "1")
+    R3 = po.ROUTES_3LANES
+    if shape == "odd_sizes_traffic":
+        cfgs = [dict(num_envs=E, num_agents=3, ego_routes=R3[:3], use_team_reward=True, traffic_flow=True, traffic_density=20.0,
+                     lidar_rays=rays, seed=1, auto_reset=ar, max_steps=25, npc_capacity=cap)
+                for E, rays, ar, cap in ((5, 72, 1, 16), (1030, 96, 2, 16), (6151, 72, 1, 8), (3, 7, 1, 32))]
+    elif shape == "max_agents_generic_rays":
+        cfgs = [dict(num_envs=7, num_agents=32, ego_routes=[R3[i % 12] for i in range(32)], traffic_flow=True, traffic_density=30.0,
+                     lidar_rays=rays, seed=2, auto_reset=1, max_steps=40, npc_capacity=32) for rays in (33, 95, 1)]
+    else:
+        cfgs = [dict(num_envs=129, num_agents=5, num_lanes=2, ego_routes=po.default_routes(2)[:5], traffic_flow=True, traffic_density=5.0,
+                     lidar_rays=96, seed=3, auto_reset=1, max_steps=30)]
+    for cfg in cfgs:
+        for lanes in ("8", "16", "32"):
+            monkeypatch.setenv("ISX_TRAFFIC_LANES", lanes)
+            b = _benv()(dict(cfg))
+            E, N = b.num_envs, b.num_agents
+            b.reset()
+            b.rollout(35)
+            snap = b.snapshot()
+            a = torch.rand(E, N, 2, device="cuda") * 2 - 1
+            for _ in range(4):
+                b.step(a)
+            m = torch.zeros(E, dtype=torch.uint8, device="cuda")
+            m[::2] = 1
+            b.reset(m); b.restore(snap, m); b.restore(snap); b.observe()
+            b.step_host(np.zeros((E, N, 2), np.float32))
+            b.set_lidar_rays(max(1, b.lidar_rays - 1))
+            b.rollout(3)
+            b.render(0)
+            b.stats()
+            assert b.check_guards() == 0, (cfg, lanes)
+            b.close()
+
+
+def test_guard_bands_do_detect_a_stray_store(monkeypatch):
+    """The detector itself: a 4-byte store just past the end of one buffer (issued from here with cudaMemset) is reported."""
+    from cuda import cudart
+    monkeypatch.setenv("ISX_GUARD", "1")
+    b = _benv()(dict(num_envs=3, num_agents=2, ego_routes=po.ROUTES_3LANES[:2]))
+    b.reset()
+    b.rollout(2)
+    assert b.check_guards() == 0
+    r = b.buf["obs"]                          # its own allocation (reward / done / status share one block)
+    (err,) = cudart.cudaMemset(r.data_ptr() + r.numel() * r.element_size(), 0, 4)
+    assert int(err) == 0
+    assert b.check_guards() == 1
+    (err,) = cudart.cudaMemset(b.buf["ego_x"].data_ptr() - 8, 0, 1)
+    assert int(err) == 0 and b.check_guards() == 2
+    b.close()
+    monkeypatch.delenv("ISX_GUARD")
+    b = _benv()(dict(num_envs=3, num_agents=2, ego_routes=po.ROUTES_3LANES[:2]))
+    with pytest.raises(Exception):
+        b.check_guards()                       # guards are off: ISX_E_STATE
+    b.close()
