@@ -136,7 +136,9 @@ typedef struct isx_stats {
 /* Environment switches read at isx_create (tuning / bisecting aids, all optional): ISX_NO_PDL=1 (fully serialised kernel
  * launches instead of programmatic dependent launch), ISX_NO_GRAPH=1 (host-buffer step on the stream path instead of the
  * captured CUDA graph), ISX_PIPE_PLAN="w0,w1,..." (env ranges of the host-step pipeline), ISX_LIDAR_CTAS_PER_SM=n (cap of
- * the persistent beam-kernel grid), ISX_HOST_THREADS=n (host threads completing obs rows), ISX_TRACE=1 (per-env phase stamps, isx_trace_read). */
+ * the persistent beam-kernel grid), ISX_HOST_THREADS=n (host threads completing obs rows), ISX_TRACE=1 (per-env phase stamps, isx_trace_read),
+ * ISX_TRAFFIC_LANES=8|16|32 (force a k_traffic instance; default: by batch size), ISX_GUARD=1 (red zones around every device
+ * buffer, isx_debug_check_guards). */
 const char *isx_last_error(void);
 int isx_abi_version(void);
 
