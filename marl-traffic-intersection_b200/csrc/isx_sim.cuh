@@ -594,6 +594,29 @@ struct BeamWindow { int ia, span, kmin; };
 // 72 beams, >1000x their error) and every candidate sample is verified exactly by ray_rect_first_hit.
 // kmin: no sample before index kmin can lie in the rectangle — a sample sits 4k px from the origin and within 1 px per
 // axis of its pixel, so 4k >= (distance to the centre) - (half diagonal of the grown rectangle); half a pixel of slack.
+// atan / atan2 for the window only: odd polynomial of degree 9 on [0, 1] (max error 1.2e-5 rad, fitted and measured in
+// float32), reciprocal for the rest of the range.  Two of them add up to < 3e-5 rad = 4e-4 beams at 96 beams, against the
+// MARGIN of 0.05 beams below (and every candidate sample is verified exactly anyway).  The library atan2f / atanf cost
+// ~55 / ~30 instructions each with their exact division and special cases; these cost ~14 / ~10.
+ISX_HD float fast_atan01(float a) {
+    const float s = a * a;
+    return a * fmaf(s, fmaf(s, fmaf(s, fmaf(s, 0.020845098f, -0.08515632f), 0.18015927f), -0.33030477f), 0.9998663f);
+}
+ISX_HD float fast_atan(float t) {
+    const float at = fabsf(t);
+    const bool big = at > 1.0f;
+    float r = fast_atan01(big ? approx_rcp(at) : at);
+    if (big) r = 1.57079632679f - r;
+    return copysignf(r, t);
+}
+ISX_HD float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float r = (mx > 0.0f) ? fast_atan01(mn * approx_rcp(mx)) : 0.0f;
+    if (ay > ax) r = 1.57079632679f - r;
+    if (x < 0.0f) r = 3.14159265359f - r;
+    return copysignf(r, y);
+}
 ISX_HD_NOINL BeamWindow beam_window(const PixRect& r, float cx, float cy, float heading, int R) {
     BeamWindow w;
     w.ia = 0; w.span = 255; w.kmin = 0;
@@ -604,7 +627,7 @@ ISX_HD_NOINL BeamWindow beam_window(const PixRect& r, float cx, float cy, float 
     const float D2 = X * X + Y * Y, rho2 = hx * hx + hy * hy;
     if (!(D2 > rho2 * 1.05f + 1.0f)) return w;
     {
-        const int km = (int)floorf((sqrtf(D2) - sqrtf(rho2) - 0.5f) * 0.25f);
+        const int km = (int)floorf((approx_sqrt(D2) - approx_sqrt(rho2) - 0.5f) * 0.25f);    // 1e-4 px of error against the 0.5
         w.kmin = km < 0 ? 0 : (km > 255 ? 255 : km);
     }
     float tmin = 0.0f, tmax = 0.0f;
@@ -618,10 +641,10 @@ ISX_HD_NOINL BeamWindow beam_window(const PixRect& r, float cx, float cy, float 
     }
     const float MARGIN = 0.05f;
     const float inv_step = (float)(R - 1) * (1.0f / 6.28318530718f);
-    float phi = atan2f(-Y, X) - heading;
+    float phi = fast_atan2(-Y, X) - heading;
     phi = phi - 6.28318530718f * floorf(phi * (1.0f / 6.28318530718f) + 0.5f);   // to [-pi, pi]
-    const float f_lo = (phi + atanf(tmin) * 1.0001f + 3.14159265359f) * inv_step;
-    const float f_hi = (phi + atanf(tmax) * 1.0001f + 3.14159265359f) * inv_step;
+    const float f_lo = (phi + fast_atan(tmin) * 1.0001f + 3.14159265359f) * inv_step;
+    const float f_hi = (phi + fast_atan(tmax) * 1.0001f + 3.14159265359f) * inv_step;
     int ia = (int)floorf(f_lo - MARGIN);
     const int ib = (int)ceilf(f_hi + MARGIN);
     const int span = ib - ia;
