@@ -233,3 +233,28 @@ def test_guard_bands_do_detect_a_stray_store(monkeypatch):
     with pytest.raises(Exception):
         b.check_guards()                       # guards are off: ISX_E_STATE
     b.close()
+
+
+@pytest.mark.parametrize("E", [640, 6144])
+def test_step_host_into_caller_buffers_equals_pinned_views(E):
+    """isx_step_host with caller-owned (pageable) output buffers — what a ctypes / cgo binding passes — against the same step
+    read from the library's pinned views, for both transports (rows copied by the copy engine below 16,384 agents, compact
+    records expanded by host threads above)."""
+    import ctypes as C
+    from marl_traffic_intersection_b200 import _lib
+    cfg = dict(num_envs=E, num_agents=3, ego_routes=po.ROUTES_3LANES[:3], traffic_flow=True, traffic_density=2.0, seed=9)
+    a_env, b_env = _benv()(cfg), _benv()(cfg)
+    rng = np.random.default_rng(3)
+    obs = np.full((E, 3, 127), np.nan, np.float32)
+    rew = np.zeros((E, 3), np.float32)
+    done, status = np.zeros((E, 3), np.uint8), np.zeros((E, 3), np.uint8)
+    term, trunc = np.zeros(E, np.uint8), np.zeros(E, np.uint8)
+    vp = lambda x: C.c_void_p(x.ctypes.data)
+    for t in range(12):
+        act = rng.uniform(-1, 1, (E, 3, 2)).astype(np.float32)
+        o1, r1, d1, s1, t1, u1 = a_env.step_host(act)
+        _lib.check(b_env._lib, b_env._lib.isx_step_host(b_env._h, vp(act), C.c_float(1.0 / 60.0), vp(obs), vp(rew), vp(done), vp(status),
+                                                      vp(term), vp(trunc), b_env._stream()))
+        assert (bits(o1) == bits(obs)).all() and (bits(r1) == bits(rew)).all(), t
+        assert (d1 == done).all() and (s1 == status).all() and (t1 == term.astype(bool)).all() and (u1 == trunc.astype(bool)).all(), t
+    a_env.close(); b_env.close()
