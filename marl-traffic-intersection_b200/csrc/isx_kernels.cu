@@ -30,7 +30,8 @@ constexpr unsigned FULL = 0xffffffffu;
 #define ISX_FEAT_THREADS 128
 #endif
 #ifndef ISX_TRAFFIC_MINB
-#define ISX_TRAFFIC_MINB 48   // 32-thread CTAs, 42 registers (with four envs per warp: 32 -> 106.9 us, 48 -> 103.2 at 65536 envs); earlier: 64 registers neutral at 8192 envs, where the
+#define ISX_TRAFFIC_MINB 48   // 32-thread CTAs; a value above the 32-CTA/SM hardware limit leaves the register count to ptxas: 72 registers,
+                              // 28 CTAs/SM, no spills (103 us at 65536 envs; capped at 64 registers = MINB 32: spills, 107 us)
 #endif                        // longest env chain sets the time, 145 -> 132 us at 65536 envs, where resident warps do
 #ifndef ISX_EGO_MINB
 #define ISX_EGO_MINB 8        // 64 registers, no spills (76.3 -> 75.1 us at 65536 envs; tighter caps spill and lose)
