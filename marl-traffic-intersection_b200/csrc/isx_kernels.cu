@@ -32,7 +32,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef ISX_TRAFFIC_MINB
 #define ISX_TRAFFIC_MINB 48   // 32-thread CTAs; a value above the 32-CTA/SM hardware limit leaves the register count to ptxas: 72 registers,
                               // 28 CTAs/SM, no spills (103 us at 65536 envs; capped at 64 registers = MINB 32: spills, 107 us)
-#endif                        // longest env chain sets the time, 145 -> 132 us at 65536 envs, where resident warps do
+#endif
 #ifndef ISX_EGO_MINB
 #define ISX_EGO_MINB 8        // 64 registers, no spills (76.3 -> 75.1 us at 65536 envs; tighter caps spill and lose)
 #endif
