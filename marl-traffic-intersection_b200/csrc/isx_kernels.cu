@@ -497,13 +497,15 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
     unsigned cmask = 0;                            // bit j: ego a collides with ego j > a (sub-warp numbering)
     for (int dlt = 1; dlt < N; ++dlt) {
         const float ox = __shfl_down_sync(FULL, p.x, dlt, NP), oy = __shfl_down_sync(FULL, p.y, dlt, NP), oh = __shfl_down_sync(FULL, p.h, dlt, NP);
-        if (is_ego && !frozen && a + dlt < N && cars_collide(p.x, p.y, p.h, ox, oy, oh)) cmask |= 1u << (a + dlt);
+        // the cheap distance reject inline (it decides nearly every pair); only close pairs pay for the out-of-line SAT
+        if (is_ego && !frozen && a + dlt < N && !cars_far_apart(p.x, p.y, ox, oy) && cars_collide(p.x, p.y, p.h, ox, oy, oh)) cmask |= 1u << (a + dlt);
     }
     bool npc_hit = false;
     if (is_ego && !frozen) {
         for (int k = 0; k < c && !npc_hit; ++k) {
             const int ni = env * d.M + k;
-            npc_hit = cars_collide(p.x, p.y, p.h, d.nx[ni], d.ny[ni], d.nh[ni]);
+            const float qx = d.nx[ni], qy = d.ny[ni];
+            if (!cars_far_apart(p.x, p.y, qx, qy)) npc_hit = cars_collide(p.x, p.y, p.h, qx, qy, d.nh[ni]);
         }
     }
     {
