@@ -441,15 +441,18 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
     float rew = 0.0f;
     int status = ISX_ALIVE;
     bool done = false;
+    float sn = 0.0f, cs = 1.0f;                    // sine / cosine of p.h, evaluated once per ego and step
+    bool have_sc = false;
     if (is_ego && !frozen) {
         if (alive) {                               // :151-163
             float thr, st;
             if (actions) { thr = actions[2 * ai]; st = actions[2 * ai + 1]; }
             else philox_action(d.seed, genv, tick, (uint32_t)a, thr, st);
-            car_update(p, steer, acc, thr, st, dt);
+            car_update_sc(p, steer, acc, thr, st, dt, &sn, &cs);       // (sn, cs) of the new heading: also the corners, the SAT, the rectangle
+            have_sc = true;
             const RouteMeta m = d.route_meta[a];
             rew = reward_base(d.rc, p.x, p.y, p.v, acc, steer, m.goal, d.max_progress, pd, pa0, pa1);
-            status = ego_self_status(d.lanes, p.x, p.y, p.h, m.goal, m.goal_prev);     // :166-290
+            status = ego_self_status_sc(d.lanes, p.x, p.y, sn, cs, m.goal, m.goal_prev);     // :166-290
             done = status != ISX_ALIVE;
         } else { status = ISX_DEAD; done = true; }
     }
@@ -493,19 +496,25 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
         }
         if (upd) pidx = bi;
     }
+    if (is_ego && !have_sc) sincosf_nc(p.h, &sn, &cs);             // dead / frozen egos (rare): their pose still takes part below
     // -- car-car override (:293-318)
     unsigned cmask = 0;                            // bit j: ego a collides with ego j > a (sub-warp numbering)
     for (int dlt = 1; dlt < N; ++dlt) {
-        const float ox = __shfl_down_sync(FULL, p.x, dlt, NP), oy = __shfl_down_sync(FULL, p.y, dlt, NP), oh = __shfl_down_sync(FULL, p.h, dlt, NP);
+        const float ox = __shfl_down_sync(FULL, p.x, dlt, NP), oy = __shfl_down_sync(FULL, p.y, dlt, NP);
+        const float os = __shfl_down_sync(FULL, sn, dlt, NP), oc = __shfl_down_sync(FULL, cs, dlt, NP);
         // the cheap distance reject inline (it decides nearly every pair); only close pairs pay for the out-of-line SAT
-        if (is_ego && !frozen && a + dlt < N && !cars_far_apart(p.x, p.y, ox, oy) && cars_collide(p.x, p.y, p.h, ox, oy, oh)) cmask |= 1u << (a + dlt);
+        if (is_ego && !frozen && a + dlt < N && !cars_far_apart(p.x, p.y, ox, oy) && cars_collide_sc(p.x, p.y, sn, cs, ox, oy, os, oc)) cmask |= 1u << (a + dlt);
     }
     bool npc_hit = false;
     if (is_ego && !frozen) {
         for (int k = 0; k < c && !npc_hit; ++k) {
             const int ni = env * d.M + k;
             const float qx = d.nx[ni], qy = d.ny[ni];
-            if (!cars_far_apart(p.x, p.y, qx, qy)) npc_hit = cars_collide(p.x, p.y, p.h, qx, qy, d.nh[ni]);
+            if (!cars_far_apart(p.x, p.y, qx, qy)) {
+                float ns, ncs;
+                sincosf_nc(d.nh[ni], &ns, &ncs);
+                npc_hit = cars_collide_sc(p.x, p.y, sn, cs, qx, qy, ns, ncs);
+            }
         }
     }
     {
@@ -545,6 +554,7 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
             const RouteMeta m = d.route_meta[a];                  // Car::respawn (Car.cpp:76-84)
             p.x = m.spawn_x; p.y = m.spawn_y; p.v = 0.0f; p.h = m.spawn_h;
             pidx = 0; pd = 0.0f; pa0 = 0.0f; pa1 = 0.0f; acc = 0.0f; steer = 0.0f;
+            sincosf_nc(p.h, &sn, &cs);                              // the rectangle below is the respawned car's
         }
         const int na = __popc(alive_m), ns = __popc(succ_m);
         term = ns > 0 && ns == na;
@@ -563,7 +573,7 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
             for (int i = 0; i < ISX_MAX_RAYS / 16; ++i) hz[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         // lidar pixel rectangle of the (possibly respawned) ego for k_features / k_lidar_obs
-        reinterpret_cast<PixRect*>(d.car_rect)[(size_t)env * (N + d.M) + a] = car_pixel_rect(p.x, p.y, p.h);
+        reinterpret_cast<PixRect*>(d.car_rect)[(size_t)env * (N + d.M) + a] = car_pixel_rect_sc(p.x, p.y, sn, cs);
     }
     if (env_ok && a == 0) {
         d.step_count[env] = step_count; d.tick[env] = tick;

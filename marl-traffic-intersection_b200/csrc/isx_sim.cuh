@@ -84,7 +84,8 @@ ISX_HD float car_steer_update(float steer, float steer_in) {                // C
     return steer + (target - steer) * 0.2f;
 }
 // tan_steer = tanf(new steering angle); only used when |v| > 0.1 (Car.cpp:27-30)
-ISX_HD void car_motion_update(Pose& p, float& acc, float throttle, float tan_steer, float dt) {   // Car.cpp:12,17-39
+// (sin_h, cos_h): sine / cosine of the NEW heading, for callers that need them again (status corners, SAT, pixel rectangle)
+ISX_HD void car_motion_update(Pose& p, float& acc, float throttle, float tan_steer, float dt, float* sin_h = nullptr, float* cos_h = nullptr) {   // Car.cpp:12,17-39
     acc = throttle * MAX_ACC;
     float v = p.v;
     if (throttle == 0.0f) v = v * 0.95f;
@@ -105,10 +106,16 @@ ISX_HD void car_motion_update(Pose& p, float& acc, float throttle, float tan_ste
     p.y = p.y - v * s;
     p.v = v;
     p.h = h;
+    if (sin_h) *sin_h = s;
+    if (cos_h) *cos_h = c;
 }
 ISX_HD_NOINL void car_update(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt) {
     steer = car_steer_update(steer, steer_in);
     car_motion_update(p, acc, throttle, tanf_nc(steer), dt);
+}
+ISX_HD_NOINL void car_update_sc(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt, float* sin_h, float* cos_h) {
+    steer = car_steer_update(steer, steer_in);
+    car_motion_update(p, acc, throttle, tanf_nc(steer), dt, sin_h, cos_h);
 }
 
 // Car::corners (Car.cpp:86-103): (+-27, +-12) rotated by +heading (no y flip) — order FL, FR, RR, RL.
@@ -149,6 +156,14 @@ ISX_HD bool cars_far_apart(float x1, float y1, float x2, float y2) {
     return dx * dx + dy * dy > 4900.0f;
 }
 
+// the same with the sines / cosines of both headings supplied (each car's heading is evaluated once per step)
+ISX_HD_NOINL bool cars_collide_sc(float x1, float y1, float s1, float c1, float x2, float y2, float s2, float c2) {
+    if (cars_far_apart(x1, y1, x2, y2)) return false;
+    float ax[4], ay[4], bx[4], by[4];
+    car_corners(x1, y1, s1, c1, ax, ay);
+    car_corners(x2, y2, s2, c2, bx, by);
+    return sat_overlap(ax, ay, s1, c1, bx, by, s2, c2);
+}
 ISX_HD_NOINL bool cars_collide(float x1, float y1, float h1, float x2, float y2, float h2) {
     if (cars_far_apart(x1, y1, x2, y2)) return false;
     float s1, c1, s2, c2;
@@ -222,14 +237,20 @@ inline void path_far_table(const F2* path, float* far2) {
 
 // ---------------------------------------------------------------- ego status (IntersectionEnv.cpp:166-290)
 // goal = path[159], prev = path[158].  Returns ISX status code of the car on its own (before car-car).
+ISX_HD_NOINL int ego_self_status_sc(int lanes, float x, float y, float s, float c, F2 goal, F2 prev);
 ISX_HD_NOINL int ego_self_status(int lanes, float x, float y, float h, F2 goal, F2 prev) {
+    float s, c;
+    sincosf_nc(h, &s, &c);
+    return ego_self_status_sc(lanes, x, y, s, c, goal, prev);
+}
+// (s, c) = sine / cosine of the heading; they are only used when the car is not in its success zone, as in the reference
+ISX_HD_NOINL int ego_self_status_sc(int lanes, float x, float y, float s, float c, F2 goal, F2 prev) {
     const float dxr = goal.x - prev.x, dyr = goal.y - prev.y;
     bool ok;
     if (fabsf(dxr) > fabsf(dyr)) ok = (fabsf(y - goal.y) < 15.0f) && (fabsf(x - goal.x) < 40.0f);
     else                         ok = (fabsf(x - goal.x) < 15.0f) && (fabsf(y - goal.y) < 40.0f);
     if (ok) return 2;  // SUCCESS
-    float s, c, cx[4], cy[4];
-    sincosf_nc(h, &s, &c);
+    float cx[4], cy[4];
     car_corners(x, y, s, c, cx, cy);
     const float lo = -100.0f, hi = (float)WIDTH + 100.0f;
 #pragma unroll
@@ -292,6 +313,12 @@ ISX_HD PixRect make_pix_rect(int x0, int x1, int y0, int y1) {
     return r;
 }
 ISX_HD bool pix_rect_empty(const PixRect& r) { return r.x0 > r.x1 || r.y0 > r.y1; }
+ISX_HD PixRect car_pixel_rect_sc(float x, float y, float s, float c) {
+    const float hl = CAR_LENGTH * 0.5f, hw = CAR_WIDTH * 0.5f;
+    const float ex = fabsf(c) * hl + fabsf(s) * hw;
+    const float ey = fabsf(s) * hl + fabsf(c) * hw;
+    return make_pix_rect((int)ceilf(x - ex), (int)floorf(x + ex), (int)ceilf(y - ey), (int)floorf(y + ey));
+}
 ISX_HD_NOINL PixRect car_pixel_rect(float x, float y, float h) {
     float s, c;
     sincosf_nc(h, &s, &c);
