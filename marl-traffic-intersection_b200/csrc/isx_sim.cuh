@@ -113,7 +113,7 @@ ISX_HD_NOINL void car_update(Pose& p, float& steer, float& acc, float throttle, 
     steer = car_steer_update(steer, steer_in);
     car_motion_update(p, acc, throttle, tanf_nc(steer), dt);
 }
-ISX_HD_NOINL void car_update_sc(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt, float* sin_h, float* cos_h) {
+ISX_HD void car_update_sc(Pose& p, float& steer, float& acc, float throttle, float steer_in, float dt, float* sin_h, float* cos_h) {
     steer = car_steer_update(steer, steer_in);
     car_motion_update(p, acc, throttle, tanf_nc(steer), dt, sin_h, cos_h);
 }
@@ -237,14 +237,14 @@ inline void path_far_table(const F2* path, float* far2) {
 
 // ---------------------------------------------------------------- ego status (IntersectionEnv.cpp:166-290)
 // goal = path[159], prev = path[158].  Returns ISX status code of the car on its own (before car-car).
-ISX_HD_NOINL int ego_self_status_sc(int lanes, float x, float y, float s, float c, F2 goal, F2 prev);
+ISX_HD int ego_self_status_sc(int lanes, float x, float y, float s, float c, F2 goal, F2 prev);
 ISX_HD_NOINL int ego_self_status(int lanes, float x, float y, float h, F2 goal, F2 prev) {
     float s, c;
     sincosf_nc(h, &s, &c);
     return ego_self_status_sc(lanes, x, y, s, c, goal, prev);
 }
 // (s, c) = sine / cosine of the heading; they are only used when the car is not in its success zone, as in the reference
-ISX_HD_NOINL int ego_self_status_sc(int lanes, float x, float y, float s, float c, F2 goal, F2 prev) {
+ISX_HD int ego_self_status_sc(int lanes, float x, float y, float s, float c, F2 goal, F2 prev) {
     const float dxr = goal.x - prev.x, dyr = goal.y - prev.y;
     bool ok;
     if (fabsf(dxr) > fabsf(dyr)) ok = (fabsf(y - goal.y) < 15.0f) && (fabsf(x - goal.x) < 40.0f);
