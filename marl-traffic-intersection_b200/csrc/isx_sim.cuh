@@ -644,7 +644,7 @@ ISX_HD float fast_atan2(float y, float x) {
     if (x < 0.0f) r = 3.14159265359f - r;
     return copysignf(r, y);
 }
-ISX_HD_NOINL BeamWindow beam_window(const PixRect& r, float cx, float cy, float heading, int R) {
+ISX_HD BeamWindow beam_window(const PixRect& r, float cx, float cy, float heading, int R) {
     BeamWindow w;
     w.ia = 0; w.span = 255; w.kmin = 0;
     if (R < 4) return w;
