@@ -157,14 +157,14 @@ ISX_HD bool cars_far_apart(float x1, float y1, float x2, float y2) {
 }
 
 // the same with the sines / cosines of both headings supplied (each car's heading is evaluated once per step)
-ISX_HD_NOINL bool cars_collide_sc(float x1, float y1, float s1, float c1, float x2, float y2, float s2, float c2) {
+ISX_HD bool cars_collide_sc(float x1, float y1, float s1, float c1, float x2, float y2, float s2, float c2) {
     if (cars_far_apart(x1, y1, x2, y2)) return false;
     float ax[4], ay[4], bx[4], by[4];
     car_corners(x1, y1, s1, c1, ax, ay);
     car_corners(x2, y2, s2, c2, bx, by);
     return sat_overlap(ax, ay, s1, c1, bx, by, s2, c2);
 }
-ISX_HD_NOINL bool cars_collide(float x1, float y1, float h1, float x2, float y2, float h2) {
+ISX_HD bool cars_collide(float x1, float y1, float h1, float x2, float y2, float h2) {
     if (cars_far_apart(x1, y1, x2, y2)) return false;
     float s1, c1, s2, c2;
     sincosf_nc(h1, &s1, &c1);
@@ -319,7 +319,7 @@ ISX_HD PixRect car_pixel_rect_sc(float x, float y, float s, float c) {
     const float ey = fabsf(s) * hl + fabsf(c) * hw;
     return make_pix_rect((int)ceilf(x - ex), (int)floorf(x + ex), (int)ceilf(y - ey), (int)floorf(y + ey));
 }
-ISX_HD_NOINL PixRect car_pixel_rect(float x, float y, float h) {
+ISX_HD PixRect car_pixel_rect(float x, float y, float h) {
     float s, c;
     sincosf_nc(h, &s, &c);
     const float hl = CAR_LENGTH * 0.5f, hw = CAR_WIDTH * 0.5f;
@@ -699,7 +699,7 @@ ISX_HD bool beam_in_window(const BeamWindow& w, int i, int R) {
 // (bit 0: eligible for the ghost-path scan, bit 1: me yields to it).  One function because both start from the same
 // centre distance hypot(dx, dy) and the same |wrap(me.h - ot.h)| — on the list-order critical path of k_traffic a
 // second hypot + fmod per NPC is ~10% of the step of the busiest env.
-ISX_HD_NOINL int npc_pair_eval(const Pose& me, const Pose& ot, float me_sin, float me_cos, float me_dc, bool me_before_ot, float* front) {
+ISX_HD int npc_pair_eval(const Pose& me, const Pose& ot, float me_sin, float me_cos, float me_dc, bool me_before_ot, float* front) {
     const float dxt = ot.x - me.x, dyt = ot.y - me.y;
     const float dto = hypotf_(dxt, dyt);
     const float ad = fabsf(wrap_angle(me.h - ot.h));
