@@ -199,6 +199,7 @@ static Dev shard_of(const Dev& d, int e0, int cnt, int shard_idx) {
     s.ncount += oE; s.next_uid += oE; s.step_count += oE; s.tick += oE;
     s.agent_rec = static_cast<char*>(d.agent_rec) + oEN * 16; s.car_rect = static_cast<char*>(d.car_rect) + oEC * sizeof(PixRect);
     s.cand += oEN * (size_t)(d.N + d.M); s.cand_n += oEN; s.ray_counter = d.ray_counter + shard_idx;
+    if (d.order) { s.order = d.order + oE; s.order_cnt = d.order_cnt + 8 * shard_idx; }
     s.obs_c += oEN * 32; s.hit_c += oEN * (size_t)d.R;
     s.obs += oEN * ISX_OBS_DIM; s.reward += oEN; s.done += oEN; s.status += oEN;
     s.terminated += oE; s.truncated += oE; s.agents_alive += oE; s.lidar_hit += oEN * ISX_MAX_RAYS;
@@ -456,6 +457,9 @@ int isx_create_groups(const isx_config* cfgs, int32_t n_groups, isx_handle** out
         float4* rec; PixRect* rc;
         ALLOC(rec, EN); ALLOC(rc, E * (size_t)(d.N + d.M)); ALLOC(d.cand, EN * (size_t)(d.N + d.M)); ALLOC(d.cand_n, EN);
         ALLOC(d.ray_counter, ISX_MAX_GROUPS + 8);
+        // env lists by NPC count for k_traffic (ISX_NO_ORDER=1: envs in index order; tuning / bisecting aid)
+        d.order = nullptr; d.order_cnt = nullptr; d.order_stride = (int)E;
+        if (getenv("ISX_NO_ORDER") == nullptr) { ALLOC(d.order, 5 * E); ALLOC(d.order_cnt, (ISX_MAX_GROUPS + 8) * 8); }
         d.agent_rec = rec; d.car_rect = rc;
     }
 #undef ALLOC

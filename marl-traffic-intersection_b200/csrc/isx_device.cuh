@@ -54,6 +54,10 @@ struct Dev {
     uint32_t* cand;              // [E][N][N+M] packed beam candidates: car | first beam << 8 | span << 16 | kmin << 24
     int* cand_n;                 // [E][N]
     unsigned* ray_counter;       // [1] dynamic work counter of k_lidar_obs
+    // ---- k_traffic_order -> k_traffic scratch (null: envs are stepped in index order)
+    int* order;                  // [5][order_stride] env ids (local to this view) by NPC count 0, 1, 2, 3, >= 4
+    unsigned* order_cnt;         // [8] fill of the five lists (zeroed by k_ego, which always follows k_traffic)
+    int order_stride;            // envs of the whole handle (list k starts at order + k * order_stride)
     // ---- outputs
     float* obs_c;                // [E][N][32]  compact record for the host-buffer step: obs[0..30] + alive flag (isx_host_expand.cpp)
     uint8_t* hit_c;              // [E][N][R]   lidar hit indices, dense stride R (what crosses PCIe instead of the float lidar columns)

@@ -359,6 +359,47 @@ __device__ __forceinline__ void traffic_env(const Dev& d, float dt, float spawn_
 // warps this latency-bound kernel has to retire (2 envs per warp: 102 -> 77 us at 32768 envs; 4 per warp: see DESIGN.md).  A group
 // of 8 lanes holds at most 8 NPCs: when an env of the warp already has 8 and room for a ninth (capacity > 8), the warp
 // steps its four envs one after the other on all 32 lanes instead (rare: the largest population observed is 13).
+// Envs that share a warp in k_traffic<8 / 16> run in lock-step for as many list-order rounds as the FULLEST of them holds
+// NPCs: in the steady state of BASELINE's C5 an env holds 0 / 1 / 2 / 3 / 4+ NPCs with probability .27 / .44 / .23 / .06 /
+// .002, so four envs in index order make a warp run 1.97 rounds on average where the mean env needs 1.07.  This kernel
+// (thread per env, just before k_traffic) files every env of the view into one of five lists by the NPC count it starts the
+// step with; k_traffic then takes its envs from the lists — fullest first (longest chains start first), equal counts side by
+// side.  Envs are independent, so the order in which they are stepped (and the arbitrary order inside a list: one
+// warp-aggregated atomic per list and warp) changes no result, only which envs share an instruction stream.
+constexpr int ORDER_LISTS = 5;
+__global__ void __launch_bounds__(256)
+k_traffic_order(const Dev d) {
+    pdl_launch_dependents();
+    pdl_wait();                                                       // keeps the launch chain transitive (k_traffic waits for THIS grid only)
+    const int env = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    int b = -1;
+    if (env < d.E) {
+        const bool reset_now = d.auto_reset && (d.terminated[env] | d.truncated[env]);
+        b = reset_now ? 0 : min(d.ncount[env], ORDER_LISTS - 1);
+    }
+#pragma unroll
+    for (int k = 0; k < ORDER_LISTS; ++k) {
+        const unsigned m = __ballot_sync(FULL, b == k);
+        if (m == 0u) continue;
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(d.order_cnt + k, (unsigned)__popc(m));
+        base = __shfl_sync(FULL, base, __ffs(m) - 1);
+        if (b == k) d.order[(size_t)k * d.order_stride + base + __popc(m & ((1u << lane) - 1u))] = env;
+    }
+}
+// slot -> env: the lists laid end to end, fullest first (slots past the last env stay idle: >= d.E)
+__device__ __forceinline__ int ordered_env(const Dev& d, int slot) {
+    if (d.order == nullptr || slot >= d.E) return slot;
+    int s = slot;
+#pragma unroll
+    for (int k = ORDER_LISTS - 1; k >= 0; --k) {
+        const int n = (int)d.order_cnt[k];
+        if (s < n) return d.order[(size_t)k * d.order_stride + s];
+        s -= n;
+    }
+    return d.E;                                                       // not reached: the lists hold every env exactly once
+}
+
 template <int L>
 __global__ void __launch_bounds__(DYN_WARPS * 32, ISX_TRAFFIC_MINB)
 k_traffic(const Dev d, float dt, float spawn_prob) {
@@ -367,19 +408,21 @@ k_traffic(const Dev d, float dt, float spawn_prob) {
     constexpr int EPW = 32 / L;                                       // envs per warp
     __shared__ NpcSmem sm_all[DYN_WARPS * EPW];
     const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
-    const int env0 = (blockIdx.x * DYN_WARPS + warp) * EPW;           // first env of this warp
+    const int env0 = (blockIdx.x * DYN_WARPS + warp) * EPW;           // first env slot of this warp
     if (env0 >= d.E) return;                                          // whole warp leaves; only warp-level sync below
     if (L < 32) {
-        const int e = env0 + wl / L;
+        const int e = ordered_env(d, env0 + wl / L);
         bool wide = false;
         if (e < d.E && d.M > L) {
             const bool reset_now = d.auto_reset && (d.terminated[e] | d.truncated[e]);
             wide = !reset_now && d.ncount[e] >= L;
         }
         if (__any_sync(FULL, wide)) {
-            for (int k = 0; k < EPW; ++k) { traffic_env<32>(d, dt, spawn_prob, env0 + k, wl, sm_all[warp * EPW]); __syncwarp(); }
+            for (int k = 0; k < EPW; ++k) { traffic_env<32>(d, dt, spawn_prob, __shfl_sync(FULL, e, k * L), wl, sm_all[warp * EPW]); __syncwarp(); }
             return;
         }
+        traffic_env<L>(d, dt, spawn_prob, e, wl, sm_all[warp * EPW + wl / L]);
+        return;
     }
     traffic_env<L>(d, dt, spawn_prob, env0 + wl / L, wl, sm_all[warp * EPW + wl / L]);
 }
@@ -400,6 +443,7 @@ k_ego(const Dev d, const float* __restrict__ actions, float dt) {
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int sub = lane / NP, a = lane % NP;
     const int env_raw = wg * EPW + sub;
+    if (d.order_cnt != nullptr && blockIdx.x == 0 && threadIdx.x < 8) d.order_cnt[threadIdx.x] = 0u;   // k_traffic is done with its env lists
     const bool env_ok = env_raw < d.E;
     const int env = env_ok ? env_raw : d.E - 1;
     const int N = d.N;
@@ -1204,6 +1248,10 @@ cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_
     // large batches by the warps to retire (32768 envs: 83.9 / 71.4 / 64.3 us); 8192 envs: 32.3 / 31.3 / 38.6
     const int forced = TRAFFIC_LANES ? TRAFFIC_LANES : d.traffic_lanes;
     const int lanes = forced ? forced : (d.E <= 4096 ? 32 : d.E <= 12288 ? 16 : 8);
+    if (lanes < 32 && d.order != nullptr) {           // envs that share a warp: filed by NPC count first (k_traffic_order)
+        const cudaError_t e = launch_pdl(k_traffic_order, (d.E + 255) / 256, 256, 0, st, d);
+        if (e != cudaSuccess) return e;
+    }
     if (lanes == 8) {                                 // four envs per warp (wide fallback inside the kernel)
         const int blocks = (d.E + 4 * DYN_WARPS - 1) / (4 * DYN_WARPS);
         return launch_pdl(k_traffic<8>, blocks, DYN_WARPS * 32, 0, st, d, dt, spawn_prob);

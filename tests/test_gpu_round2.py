@@ -258,3 +258,41 @@ def test_step_host_into_caller_buffers_equals_pinned_views(E):
         assert (bits(o1) == bits(obs)).all() and (bits(r1) == bits(rew)).all(), t
         assert (d1 == done).all() and (s1 == status).all() and (t1 == term.astype(bool)).all() and (u1 == trunc.astype(bool)).all(), t
     a_env.close(); b_env.close()
+
+
+def test_traffic_env_order_changes_no_result(monkeypatch):
+    """k_traffic<8 / 16> takes its envs from lists filed by NPC count (k_traffic_order) instead of in index order.  The
+    same batches — big enough for the library to pick the packed instances by itself, two groups with different settings,
+    next-step auto-reset, a masked reset, a host-buffer step cut into pipeline ranges — stepped with the lists
+    (default) and without (ISX_NO_ORDER=1) must end bit-identical in every buffer and counter."""
+    import torch
+    cfgs = [dict(num_envs=5003, num_agents=2, num_lanes=3, ego_routes=R3[:2], traffic_flow=True, traffic_density=6.0, seed=4,
+                 auto_reset=2, max_steps=90, npc_capacity=16),
+            dict(num_envs=9001, num_agents=2, num_lanes=3, ego_routes=R3[2:4], traffic_flow=True, traffic_density=1.0, seed=5,
+                 auto_reset=1, max_steps=70, npc_capacity=16)]
+    ends = []
+    for no_order in (False, True):
+        if no_order:
+            monkeypatch.setenv("ISX_NO_ORDER", "1")
+        else:
+            monkeypatch.delenv("ISX_NO_ORDER", raising=False)
+        b = _benv()([dict(c) for c in cfgs])
+        E, N = b.num_envs, b.num_agents
+        b.reset()
+        b.rollout(120)
+        m = torch.zeros(E, dtype=torch.uint8, device="cuda")
+        m[::3] = 1
+        b.reset(m)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        for _ in range(5):
+            b.step(torch.rand(E, N, 2, device="cuda", generator=g) * 2 - 1)
+        b.step_host(np.full((E, N, 2), 0.25, np.float32))
+        b.rollout(60)
+        torch.cuda.synchronize()
+        ends.append(({k: b.buf[k].cpu().numpy().copy() for k in ("obs", "reward", "status", "npc_count", "events", "lidar_hit", "terminated", "truncated")},
+                     b.stats()))
+        b.close()
+    (a, sa), (c, sc) = ends
+    assert sa == sc and sa["npc_spawned"] > 1000 and sa["env_resets"] > 1000
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint8), c[k].view(np.uint8)), k
