@@ -133,7 +133,7 @@ typedef struct isx_stats {
     int64_t neighbor_tie_sorts;  /* observations whose neighbour order needed the exact std::sort replay (equal distances, > 16 neighbours) */
 } isx_stats;
 
-/* Environment switches read at isx_create (tuning / bisecting aids, all optional): ISX_NO_PDL=1 (fully serialised kernel
+/* Environment switches read at isx_create (tuning / bisecting aids, all optional): ISX_NO_ORDER=1 (k_traffic steps its envs in index order instead of by NPC count), ISX_NO_PDL=1 (fully serialised kernel
  * launches instead of programmatic dependent launch), ISX_NO_GRAPH=1 (host-buffer step on the stream path instead of the
  * captured CUDA graph), ISX_PIPE_PLAN="w0,w1,..." (env ranges of the host-step pipeline), ISX_LIDAR_CTAS_PER_SM=n (cap of
  * the persistent beam-kernel grid), ISX_HOST_THREADS=n (host threads completing obs rows), ISX_TRACE=1 (per-env phase stamps, isx_trace_read),

@@ -794,7 +794,7 @@ static int enqueue_pinned_step(isx_handle* h, float dt, cudaStream_t st, std::ve
 // kernels of shard c+1 run while the copy engine drains the obs rows of shard c (obs is 127 floats per agent — the
 // copy, not the simulation, bounds the end-to-end rate).  Results land in the handle's pinned staging buffers
 // (isx_host_views); actions are taken from the pinned `actions` view.  Synchronous on return.
-// The whole step (1 + shards copies in, 4 kernels and 1 copy out per shard, the fork/join events) is captured ONCE per
+// The whole step (1 + shards copies in, 4–5 kernels and 1 copy out per shard, the fork/join events) is captured ONCE per
 // dt into a CUDA graph and replayed with a single launch: issuing ~35 runtime calls per step from the host costs more
 // than the first shards take to run.  ISX_NO_GRAPH=1 at isx_create keeps the plain stream path.
 // One host-buffer step whose obs rows land in `dst` ([E*N][127] floats in host memory).  Synchronous.

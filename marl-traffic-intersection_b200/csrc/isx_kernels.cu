@@ -2,7 +2,8 @@
 //
 //   k_traffic   : 8 lanes per env, four envs per warp.  NPC traffic flow (spawn draw, Gauss-Seidel planner/integrator in list order,
 //                 NPC-NPC SAT, ordered erase), lanes spread over ghost-path points / other NPCs / path-window
-//                 points.  Replaces TrafficFlow.cpp:317-367.  Only launched with traffic flow on.
+//                 points.  Replaces TrafficFlow.cpp:317-367.  Only launched with traffic flow on.  Envs that share a warp are
+//                 taken from lists filed by NPC count (k_traffic_order, one thread per env, just before).
 //   k_ego       : one LANE per ego, an env = a sub-warp of 2^ceil(log2 N) lanes: physics, reward, status, car-car
 //                 override, bonuses, team mix, respawn, termination.  Replaces IntersectionEnv.cpp:137-370.
 //   k_features  : FOUR lanes per ego: the 31 ego/neighbour observation features + the per-ego list of cars its

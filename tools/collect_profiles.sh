@@ -27,7 +27,7 @@ for r in rows[1:]:
     t[re.sub(r"\(.*", "", r[ik]).replace("void ", "")].append(v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v))
 step = {k: v for k, v in t.items() if "isx::" in k}
 tot = sum(sum(v) / len(v) for v in step.values())
-o = ["ncu --metrics gpu__time_duration.sum --clock-control none -s 1650 -c 160 : python bench.py --steps 20 --warmup 5 --no-cpu-baseline --config C5   (65536 envs x 8 agents, steady state after the 400-step pre-roll; final build)",
+o = ["ncu --metrics gpu__time_duration.sum --clock-control none -s 2060 -c 192 : python bench.py --steps 20 --warmup 5 --no-cpu-baseline --config C5   (65536 envs x 8 agents, steady state after the 400-step pre-roll; final build)",
      "(the at::FillFunctor launches are bench.py's L2 flush between timed steps, outside the event pairs; per-launch times under ncu are serialised and cold-cache: compare SHARES)"]
 for k, v in sorted(t.items(), key=lambda kv: -sum(kv[1]) / len(kv[1])):
     m = sum(v) / len(v)
