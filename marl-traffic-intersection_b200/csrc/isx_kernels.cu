@@ -54,6 +54,10 @@ constexpr int LID_THREADS = 256;
 #define ISX_TRAFFIC_LANES 0     // 0: chosen per launch by batch size (launch_traffic)
 #endif
 constexpr int TRAFFIC_LANES = ISX_TRAFFIC_LANES;   // lanes per env in k_traffic: 8 (four envs per warp), 16, 32, or 0 = by batch size
+#ifndef ISX_GHOST_PTS
+#define ISX_GHOST_PTS 2     // k_traffic ghost-path scan: blocks of L points a group tests per pass
+#endif
+constexpr int GHOST_PTS = ISX_GHOST_PTS;
 #ifndef ISX_WARP_GRAB
 #define ISX_WARP_GRAB 3
 #endif
@@ -267,28 +271,37 @@ __device__ __forceinline__ void traffic_env(const Dev& d, float dt, float spawn_
         if (__any_sync(FULL, elig != 0u)) {                        // ghost-path scan (:91-185), L points per pass
             const float safe_sq = (CAR_WIDTH * 2.0f) * (CAR_WIDTH * 2.0f);
             const int s1 = min(mp0 + 120, PATH_LEN);
-            for (int base = mp0;; base += L) {
+            // GHOST_PTS blocks of L points per pass: the pass is a dependent chain (load, test, ballot, branch), and most scans
+            // run all 120 points without a conflict — fewer, wider passes; the first conflict in index order still wins
+            for (int base = mp0;; base += GHOST_PTS * L) {
                 const bool go = elig != 0u && base < s1 && !conflict;
                 if (!__any_sync(FULL, go)) break;
-                const int gp_i = base + lane;
-                bool hit = false;
-                float dtc = 0.0f;
-                if (go && gp_i < s1) {
-                    const F2 gp = path[gp_i];
-                    unsigned near_yield = 0, near_any = 0;
-                    for (unsigned mm = elig; mm; mm &= mm - 1) {
-                        const int o = __ffs(mm) - 1;
-                        const float dx = sm.x[o] - gp.x, dy = sm.y[o] - gp.y;
-                        if (dx * dx + dy * dy < safe_sq) { near_any = 1; near_yield |= (yld >> o) & 1u; }
-                    }
-                    if (near_any) {
-                        dtc = hypotf_nc(gp.x - me.x, gp.y - me.y);
-                        hit = near_yield || (dtc < 15.0f);
+                bool hit[GHOST_PTS];
+                float dtc[GHOST_PTS];
+#pragma unroll
+                for (int jb = 0; jb < GHOST_PTS; ++jb) {
+                    const int gp_i = base + jb * L + lane;
+                    hit[jb] = false; dtc[jb] = 0.0f;
+                    if (go && gp_i < s1) {
+                        const F2 gp = path[gp_i];
+                        unsigned near_yield = 0, near_any = 0;
+                        for (unsigned mm = elig; mm; mm &= mm - 1) {
+                            const int o = __ffs(mm) - 1;
+                            const float dx = sm.x[o] - gp.x, dy = sm.y[o] - gp.y;
+                            if (dx * dx + dy * dy < safe_sq) { near_any = 1; near_yield |= (yld >> o) & 1u; }
+                        }
+                        if (near_any) {
+                            dtc[jb] = hypotf_nc(gp.x - me.x, gp.y - me.y);
+                            hit[jb] = near_yield || (dtc[jb] < 15.0f);
+                        }
                     }
                 }
-                const unsigned hb = g.ballot(hit);
-                const float first_dtc = g.shfl(dtc, hb ? __ffs(hb) - 1 : 0);
-                if (hb) { conflict = true; min_conf = first_dtc; }
+#pragma unroll
+                for (int jb = 0; jb < GHOST_PTS; ++jb) {
+                    const unsigned hb = g.ballot(hit[jb]);
+                    const float first_dtc = g.shfl(dtc[jb], hb ? __ffs(hb) - 1 : 0);
+                    if (hb && !conflict) { conflict = true; min_conf = first_dtc; }
+                }
             }
         }
         if (i == 0) ISX_STAMP(9);

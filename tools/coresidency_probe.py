@@ -9,7 +9,8 @@ import time
 import torch
 
 sys.path.insert(0, ".")
-from bench import N_AGENTS, ROUTES8  # noqa: E402
+from bench import R3  # noqa: E402
+N_AGENTS, ROUTES8 = 8, R3[:8]
 from marl_traffic_intersection_b200 import BatchedIntersectionEnv  # noqa: E402
 
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 65536

@@ -5,7 +5,8 @@ os.environ["ISX_TRACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from bench import N_AGENTS, ROUTES8
+from bench import R3
+N_AGENTS, ROUTES8 = 8, R3[:8]
 from marl_traffic_intersection_b200 import BatchedIntersectionEnv, _lib
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 env = BatchedIntersectionEnv({"num_envs": E, "num_agents": N_AGENTS, "num_lanes": 3, "ego_routes": ROUTES8, "traffic_flow": True,
