@@ -364,8 +364,8 @@ def main():
     ms_max = timed_rollout(env, K)
     t_wall = time.perf_counter() - t_wall0
     value = E * N_AGENTS * K * world / (ms_max * 1e-3)
-    # k_traffic_order + k_traffic (traffic on; the env lists exist for the packed instances, i.e. above 4096 envs), k_ego, k_features, k_lidar_obs
-    launches_per_step = (5 if E > 4096 and not os.environ.get("ISX_NO_ORDER") else 4) if cfg["traffic"] else 3
+    # k_traffic_order + k_traffic (traffic on; the env lists exist for the packed instances, i.e. above 12,288 envs), k_ego, k_features, k_lidar_obs
+    launches_per_step = (5 if E > 12288 and not os.environ.get("ISX_NO_ORDER") else 4) if cfg["traffic"] else 3
 
     # ---------------- per-kernel time for the roofline line (CUDA events around each launch, live, same state)
     kr = min(K, 200)

@@ -1258,10 +1258,12 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_t st) {
     if (!d.traffic) return cudaSuccess;
     // lanes per env by batch size (ISX_TRAFFIC_LANES = 8 / 16 / 32 forces one): small batches are bound by the list-order chain
-    // of the busiest env, which is shortest with a whole warp per env (4096 envs: 23.6 us at 32 lanes, 28.2 at 16, 36.2 at 8);
-    // large batches by the warps to retire (32768 envs: 83.9 / 71.4 / 64.3 us); 8192 envs: 32.3 / 31.3 / 38.6
+    // of the busiest env, which is shortest with a whole warp per env; large batches by the warps to retire, and the packed
+    // instances take their envs from the lists of k_traffic_order.  Measured with the lists (us at 32 / 16 / 8 lanes; profiles/r02/
+    // ab_traffic_lanes_by_batch_ordered.log): 8192 envs 27.9 / 33.6 / 44.6, 12288: 33.6 / 37.4 / 49.1, 16384: 40.4 / 40.9 / 52.6,
+    // 24576: 54.0 / 45.1 / 56.9, 32768: 66.4 / 50.3 / 59.4, 65536: - / 82.8 / 70.8
     const int forced = TRAFFIC_LANES ? TRAFFIC_LANES : d.traffic_lanes;
-    const int lanes = forced ? forced : (d.E <= 4096 ? 32 : d.E <= 12288 ? 16 : 8);
+    const int lanes = forced ? forced : (d.E <= 12288 ? 32 : d.E <= 49152 ? 16 : 8);
     if (lanes < 32 && d.order != nullptr) {           // envs that share a warp: filed by NPC count first (k_traffic_order)
         const cudaError_t e = launch_pdl(k_traffic_order, (d.E + 255) / 256, 256, 0, st, d);
         if (e != cudaSuccess) return e;
