@@ -260,9 +260,10 @@ def test_step_host_into_caller_buffers_equals_pinned_views(E):
     a_env.close(); b_env.close()
 
 
-def test_traffic_env_order_changes_no_result(monkeypatch):
+@pytest.mark.parametrize("lanes", ["8", "16"])
+def test_traffic_env_order_changes_no_result(lanes, monkeypatch):
     """k_traffic<8 / 16> takes its envs from lists filed by NPC count (k_traffic_order) instead of in index order.  The
-    same batches — big enough for the library to pick the packed instances by itself, two groups with different settings,
+    same batches — two groups with different settings, the packed instance forced (the library picks it above 12,288 envs),
     next-step auto-reset, a masked reset, a host-buffer step cut into pipeline ranges — stepped with the lists
     (default) and without (ISX_NO_ORDER=1) must end bit-identical in every buffer and counter."""
     import torch
@@ -271,6 +272,7 @@ def test_traffic_env_order_changes_no_result(monkeypatch):
             dict(num_envs=9001, num_agents=2, num_lanes=3, ego_routes=R3[2:4], traffic_flow=True, traffic_density=1.0, seed=5,
                  auto_reset=1, max_steps=70, npc_capacity=16)]
     ends = []
+    monkeypatch.setenv("ISX_TRAFFIC_LANES", lanes)
     for no_order in (False, True):
         if no_order:
             monkeypatch.setenv("ISX_NO_ORDER", "1")
