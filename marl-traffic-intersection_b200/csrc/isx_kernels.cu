@@ -379,27 +379,38 @@ __device__ __forceinline__ void traffic_env(const Dev& d, float dt, float spawn_
 // (thread per env, just before k_traffic) files every env of the view into one of five lists by the NPC count it starts the
 // step with; k_traffic then takes its envs from the lists — fullest first (longest chains start first), equal counts side by
 // side.  Envs are independent, so the order in which they are stepped (and the arbitrary order inside a list: one
-// warp-aggregated atomic per list and warp) changes no result, only which envs share an instruction stream.
+// CTA-aggregated atomic per list) changes no result, only which envs share an instruction stream.
 constexpr int ORDER_LISTS = 5;
-__global__ void __launch_bounds__(256)
+constexpr int ORDER_THREADS = 1024;
+__global__ void __launch_bounds__(ORDER_THREADS)
 k_traffic_order(const Dev d) {
     pdl_launch_dependents();
     pdl_wait();                                                       // keeps the launch chain transitive (k_traffic waits for THIS grid only)
-    const int env = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    // one atomic per list and CTA (a warp-aggregated one per warp put 2048 atomics on the same word at 65,536 envs: the
+    // kernel took as long as those took to serialise)
+    __shared__ unsigned s_cnt[ORDER_THREADS / 32][ORDER_LISTS];       // per warp: envs it files into list k, then its offset in the CTA's share
+    __shared__ unsigned s_base[ORDER_LISTS];
+    const int env = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int b = -1;
     if (env < d.E) {
         const bool reset_now = d.auto_reset && (d.terminated[env] | d.truncated[env]);
         b = reset_now ? 0 : min(d.ncount[env], ORDER_LISTS - 1);
     }
+    unsigned mine = 0;                                                // lanes below me that go to my list
 #pragma unroll
     for (int k = 0; k < ORDER_LISTS; ++k) {
         const unsigned m = __ballot_sync(FULL, b == k);
-        if (m == 0u) continue;
-        unsigned base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(d.order_cnt + k, (unsigned)__popc(m));
-        base = __shfl_sync(FULL, base, __ffs(m) - 1);
-        if (b == k) d.order[(size_t)k * d.order_stride + base + __popc(m & ((1u << lane) - 1u))] = env;
+        if (lane == 0) s_cnt[warp][k] = (unsigned)__popc(m);
+        if (b == k) mine = (unsigned)__popc(m & ((1u << lane) - 1u));
     }
+    __syncthreads();
+    if (threadIdx.x < ORDER_LISTS) {
+        unsigned tot = 0;
+        for (int w = 0; w < ORDER_THREADS / 32; ++w) { const unsigned c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = tot; tot += c; }
+        s_base[threadIdx.x] = tot ? atomicAdd(d.order_cnt + threadIdx.x, tot) : 0u;
+    }
+    __syncthreads();
+    if (b >= 0) d.order[(size_t)b * d.order_stride + s_base[b] + s_cnt[warp][b] + mine] = env;
 }
 // slot -> env: the lists laid end to end, fullest first (slots past the last env stay idle: >= d.E)
 __device__ __forceinline__ int ordered_env(const Dev& d, int slot) {
@@ -1265,7 +1276,7 @@ cudaError_t launch_traffic(const Dev& d, float dt, float spawn_prob, cudaStream_
     const int forced = TRAFFIC_LANES ? TRAFFIC_LANES : d.traffic_lanes;
     const int lanes = forced ? forced : (d.E <= 12288 ? 32 : d.E <= 49152 ? 16 : 8);
     if (lanes < 32 && d.order != nullptr) {           // envs that share a warp: filed by NPC count first (k_traffic_order)
-        const cudaError_t e = launch_pdl(k_traffic_order, (d.E + 255) / 256, 256, 0, st, d);
+        const cudaError_t e = launch_pdl(k_traffic_order, (d.E + ORDER_THREADS - 1) / ORDER_THREADS, ORDER_THREADS, 0, st, d);
         if (e != cudaSuccess) return e;
     }
     if (lanes == 8) {                                 // four envs per warp (wide fallback inside the kernel)
